@@ -1,0 +1,11 @@
+"""fluid_b200 -- B200 (sm_100a) implementation of the per-step hot path of
+TheFellow/fluid's Go package pkg/fluid, behind that package's own API.
+
+``Fluid`` mirrors ``fluid.Fluid`` (pkg/fluid/fluid.go:11-40) method for method;
+all arithmetic runs in libfluidb200.so (hand-written CUDA, C ABI in
+include/fluidb200.h).  Importing this package fails if that library is absent:
+there is no CPU path.
+"""
+from . import edits, presets  # noqa: F401
+from ._lib import FluidError, SOLVER_EXACT, SOLVER_REDBLACK  # noqa: F401
+from .fluid import Fluid, New, ScalarField, VectorField  # noqa: F401

@@ -1,0 +1,882 @@
+// fluidb200.cu -- host side of libfluidb200.so: handle lifecycle, phase driver and
+// the C ABI declared in include/fluidb200.h.  The phase order and the buffer
+// semantics follow (*Fluid).Simulate, pkg/fluid/fluid.go:79-109 of the reference.
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define FB_VERSION 100
+
+enum { SCR_CURL = 0, SCR_A, SCR_B, SCR_C, SCR_D, SCR_E, SCR_F, SCR_BKU, SCR_BKV, SCR_NOISEU, SCR_NOISEV, SCR_VIEW, SCR_N };
+
+struct fb_handle {
+    fb_config cfg;
+    Grid g;
+    int device;
+    cudaStream_t stream;
+    size_t plane_floats;          // floats per device plane
+    float *f[FB_NFIELDS];
+    float *scr[SCR_N];
+    bool noise_ready;
+    float *mirror[FB_NFIELDS];    // pinned host mirrors (lazy)
+    unsigned *d_red;              // 64 reduction slots
+    unsigned *h_red;              // pinned copy
+    int *d_bad;                   // halo-violation flag
+    // exact-solver scheduling state
+    int2 *d_order; int ntiles, nTa, nTb, order_T;
+    int *d_tile_counter; int *d_done; int epoch;
+    fb_edit_cmd *d_cmds; size_t d_cmds_cap;
+    cudaEvent_t ev0, ev1;
+    uint64_t launches;
+    fb_solve_stats stats;
+    std::string err;
+};
+
+// ---- error plumbing -----------------------------------------------------------
+static int fail(fb_handle *h, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (h) {
+        h->err = what;
+        if (e != cudaSuccess) { h->err += ": "; h->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(h, FB_ERR_CUDA, #call, _e); } while (0)
+#define CKL(what) do { h->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return fail(h, FB_ERR_CUDA, what, _e); } while (0)
+#define TRY(expr) do { int _s = (expr); if (_s != FB_OK) return _s; } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+static int scratch(fb_handle *h, int which, float **out)
+{
+    if (!h->scr[which]) {
+        CK(cudaMalloc(&h->scr[which], h->plane_floats * sizeof(float)));
+        CK(cudaMemsetAsync(h->scr[which], 0, h->plane_floats * sizeof(float), h->stream));
+    }
+    *out = h->scr[which];
+    return FB_OK;
+}
+
+// rows x columns launch geometry for full-plane kernels: x along j (unit stride)
+static inline void plane_launch(const Grid &g, int ib, int ie, dim3 &grid, dim3 &block, int cols = -1)
+{
+    block = dim3(128, 2, 1);
+    if (cols < 0) cols = g.NY;
+    grid = dim3(cdiv(cols, block.x), cdiv(ie - ib, block.y), 1);
+}
+
+// ---- lifecycle ------------------------------------------------------------------
+extern "C" int fb_version(void) { return FB_VERSION; }
+
+extern "C" int fb_default_params(fb_params *p)
+{
+    if (!p) return FB_ERR_INVALID;
+    p->relaxation = 1.9f;             // fluid.go:8
+    p->confinement = 0.0f;            // fluid.go:59
+    p->viscosity_diffusion = 0.0f;    // fluid.go:60
+    p->pressure_damping = 1.0f;       // fluid.go:61
+    p->turbulence_strength = 0.02f;   // fluid.go:62
+    p->smoke_advection = 1.0f;        // fluid.go:63
+    p->use_multigrid = 0;             // fluid.go:64
+    p->multigrid_levels = 2;          // fluid.go:65
+    p->use_bfecc = 0;                 // fluid.go:66
+    p->solver = FB_SOLVER_EXACT;
+    p->iters = 8;                     // fluid.go:81
+    return FB_OK;
+}
+
+extern "C" int fb_create(const fb_config *cfg, fb_handle **out)
+{
+    if (!cfg || !out) return FB_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->width < 1 || cfg->height < 1) return FB_ERR_INVALID;
+    const int nranks = cfg->nranks < 1 ? 1 : cfg->nranks;
+    if (cfg->rank < 0 || cfg->rank >= nranks) return FB_ERR_INVALID;
+    fb_handle *h = new (std::nothrow) fb_handle();
+    if (!h) return FB_ERR_NOMEM;
+    h->cfg = *cfg;
+    h->cfg.nranks = nranks;
+    h->device = cfg->device;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) { fprintf(stderr, "fluidb200: cudaSetDevice(%d): %s\n", h->device, cudaGetErrorString(e)); delete h; return FB_ERR_CUDA; }
+
+    Grid &g = h->g;
+    g.NX = cfg->width + 2;
+    g.NY = cfg->height + 2;
+    g.pitch = cdiv(g.NY, 32) * 32;
+    // slab decomposition of the interior lines 1..NX-2 over ranks; the ring lines
+    // i = 0 and i = NX-1 go to the first / last rank.
+    {
+        const long long W = cfg->width;
+        const long long lo = 1 + W * cfg->rank / nranks, hi = 1 + W * (cfg->rank + 1) / nranks;
+        g.i_lo = (int)lo; g.i_hi = (int)hi;
+        if (cfg->rank == 0) g.i_lo = 0;
+        if (cfg->rank == nranks - 1) g.i_hi = g.NX;
+    }
+    int ghost = nranks > 1 ? (cfg->ghost > 0 ? cfg->ghost : 32) : 0;
+    h->cfg.ghost = ghost;
+    g.i_alloc0 = g.i_lo - ghost < 0 ? 0 : g.i_lo - ghost;
+    const int alloc_end = g.i_hi + ghost > g.NX ? g.NX : g.i_hi + ghost;
+    g.lines_alloc = alloc_end - g.i_alloc0;
+    h->plane_floats = (size_t)g.lines_alloc * (size_t)g.pitch;
+
+#define CKC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { fprintf(stderr, "fluidb200: %s: %s\n", #call, cudaGetErrorString(_e)); fb_destroy(h); return _e == cudaErrorMemoryAllocation ? FB_ERR_NOMEM : FB_ERR_CUDA; } } while (0)
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < FB_NFIELDS; k++) {
+        CKC(cudaMalloc(&h->f[k], h->plane_floats * sizeof(float)));
+        CKC(cudaMemsetAsync(h->f[k], 0, h->plane_floats * sizeof(float), h->stream));   // New(): all zero => all solid
+    }
+    CKC(cudaMalloc(&h->d_red, 64 * sizeof(unsigned)));
+    CKC(cudaMemsetAsync(h->d_red, 0, 64 * sizeof(unsigned), h->stream));
+    CKC(cudaMallocHost(&h->h_red, 64 * sizeof(unsigned)));
+    CKC(cudaMalloc(&h->d_bad, sizeof(int)));
+    CKC(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+    CKC(cudaMalloc(&h->d_tile_counter, sizeof(int)));
+    CKC(cudaEventCreate(&h->ev0));
+    CKC(cudaEventCreate(&h->ev1));
+    CKC(cudaStreamSynchronize(h->stream));
+#undef CKC
+    *out = h;
+    return FB_OK;
+}
+
+extern "C" int fb_destroy(fb_handle *h)
+{
+    if (!h) return FB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < FB_NFIELDS; k++) { if (h->f[k]) cudaFree(h->f[k]); if (h->mirror[k]) cudaFreeHost(h->mirror[k]); }
+    for (int k = 0; k < SCR_N; k++) if (h->scr[k]) cudaFree(h->scr[k]);
+    if (h->d_red) cudaFree(h->d_red);
+    if (h->h_red) cudaFreeHost(h->h_red);
+    if (h->d_bad) cudaFree(h->d_bad);
+    if (h->d_order) cudaFree(h->d_order);
+    if (h->d_tile_counter) cudaFree(h->d_tile_counter);
+    if (h->d_done) cudaFree(h->d_done);
+    if (h->d_cmds) cudaFree(h->d_cmds);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return FB_OK;
+}
+
+extern "C" const char *fb_last_error(const fb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int fb_dims(const fb_handle *h, int64_t *nx, int64_t *ny, int64_t *i_lo, int64_t *i_hi)
+{
+    if (!h) return FB_ERR_INVALID;
+    if (nx) *nx = h->g.NX;
+    if (ny) *ny = h->g.NY;
+    if (i_lo) *i_lo = h->g.i_lo;
+    if (i_hi) *i_hi = h->g.i_hi;
+    return FB_OK;
+}
+
+extern "C" int fb_ghost_lines(const fb_handle *h, int32_t *ghost)
+{
+    if (!h || !ghost) return FB_ERR_INVALID;
+    *ghost = h->cfg.ghost;
+    return FB_OK;
+}
+
+extern "C" int fb_stream(fb_handle *h, void **s) { if (!h || !s) return FB_ERR_INVALID; *s = (void *)h->stream; return FB_OK; }
+
+extern "C" int fb_synchronize(fb_handle *h)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return FB_OK;
+}
+
+extern "C" int fb_timer_start(fb_handle *h)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    return FB_OK;
+}
+
+extern "C" int fb_timer_stop(fb_handle *h, float *ms)
+{
+    if (!h || !ms) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return FB_OK;
+}
+
+extern "C" int fb_launch_count(const fb_handle *h, uint64_t *count)
+{
+    if (!h || !count) return FB_ERR_INVALID;
+    *count = h->launches;
+    return FB_OK;
+}
+
+// ---- small building blocks --------------------------------------------------------
+// Compute range of this rank for a phase: owned lines widened by `extra` ghost
+// lines (clipped to what is allocated and to the domain).
+static inline void range(const fb_handle *h, int extra, int &ib, int &ie)
+{
+    const Grid &g = h->g;
+    ib = g.i_lo - extra; ie = g.i_hi + extra;
+    if (ib < g.i_alloc0) ib = g.i_alloc0;
+    if (ie > g.i_alloc0 + g.lines_alloc) ie = g.i_alloc0 + g.lines_alloc;
+}
+
+static int copy_plane(fb_handle *h, float *dst, const float *src)
+{
+    CK(cudaMemcpyAsync(dst, src, h->plane_floats * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    return FB_OK;
+}
+
+static int copy_border(fb_handle *h, float *dst, const float *src)
+{
+    int ib, ie; range(h, h->cfg.ghost, ib, ie);
+    const int n = (ie - ib) + 2 * h->g.NY;
+    k_copy_border<<<cdiv(n, 256), 256, 0, h->stream>>>(h->g, dst, src, ib, ie);
+    CKL("k_copy_border");
+    return FB_OK;
+}
+
+static int check_bad(fb_handle *h)
+{
+    if (h->cfg.nranks <= 1) return FB_OK;   // single GPU: every tap is resident
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (bad) {
+        CK(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+        return fail(h, FB_ERR_HALO, "semi-Lagrangian trace left the ghost zone; create the handle with more ghost lines");
+    }
+    return FB_OK;
+}
+
+// ---- projection -------------------------------------------------------------------
+static void omega_schedule(const fb_params *p, unsigned iters, float *omega)
+{
+    // fluid.go:162-170 (float32 arithmetic; this TU is compiled with --fmad=false)
+    const float initial = p->relaxation;
+    const float minRelax = 1.2f;
+    for (unsigned it = 0; it < iters && it < 32; it++) {
+        volatile float prog = (float)it / (float)iters;
+        volatile float t = (initial - minRelax) * prog;
+        omega[it] = initial - t;
+    }
+}
+
+static int ensure_order(fb_handle *h)
+{
+    const Grid &g = h->g;
+    if (h->d_order) return FB_OK;
+    const int T = WF_TMAX;
+    h->nTa = cdiv(g.NX - 2 + T - 1, WF_TI);
+    h->nTb = cdiv(g.NY - 2 + T - 1, WF_TJ);
+    h->ntiles = h->nTa * h->nTb;
+    std::vector<int2> order;
+    order.reserve(h->ntiles);
+    for (int d = 0; d <= h->nTa + h->nTb - 2; d++)
+        for (int a = 0; a < h->nTa; a++) {
+            const int b = d - a;
+            if (b < 0 || b >= h->nTb) continue;
+            order.push_back(make_int2(a, b));
+        }
+    CK(cudaMalloc(&h->d_order, sizeof(int2) * (size_t)h->ntiles));
+    CK(cudaMemcpyAsync(h->d_order, order.data(), sizeof(int2) * (size_t)h->ntiles, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMalloc(&h->d_done, sizeof(int) * (size_t)h->ntiles));
+    CK(cudaMemsetAsync(h->d_done, 0, sizeof(int) * (size_t)h->ntiles, h->stream));
+    h->epoch = 0;
+    return FB_OK;
+}
+
+// Run sweeps [first, first+count) of an `iters`-sweep solve, fused WF_TMAX at a time.
+static int exact_sweeps(fb_handle *h, const SolveParams &base, int first, int count)
+{
+    TRY(ensure_order(h));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    int done = 0;
+    while (done < count) {
+        const int T = (count - done) < WF_TMAX ? (count - done) : WF_TMAX;
+        SolveParams sp = base;
+        sp.sweeps = T;
+        sp.sweep0 = first + done;
+        CK(cudaMemsetAsync(h->d_tile_counter, 0, sizeof(int), h->stream));
+        h->epoch++;
+        int grid = h->ntiles < nsm * 4 ? h->ntiles : nsm * 4;
+        k_gs_wavefront<<<grid, dim3(WF_TI, T, 1), 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P], sp,
+                                                                 h->d_order, h->ntiles, h->nTb, h->d_tile_counter,
+                                                                 h->d_done, h->epoch, h->d_red);
+        CKL("k_gs_wavefront");
+        done += T;
+    }
+    return FB_OK;
+}
+
+static int read_stats(fb_handle *h, unsigned iters)
+{
+    CK(cudaMemcpyAsync(h->h_red, h->d_red, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (unsigned k = 0; k < 32; k++) {
+        float v; unsigned b = h->h_red[k];
+        memcpy(&v, &b, 4);
+        h->stats.max_div[k] = k < iters ? v : 0.0f;
+    }
+    return FB_OK;
+}
+
+// makeIncompressible (fluid.go:144-155) + solveSingleGrid (fluid.go:157-186)
+static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsigned iters)
+{
+    if (p->use_multigrid && p->multigrid_levels > 1)
+        return fail(h, FB_ERR_UNSUPPORTED, "multigrid V-cycle (fluid.go:560-758) is out of scope for this build");
+    if (iters > 32) return fail(h, FB_ERR_INVALID, "at most 32 sweeps per solve");
+    TRY(copy_border(h, h->f[FB_NEWU], h->f[FB_U]));
+    TRY(copy_border(h, h->f[FB_NEWV], h->f[FB_V]));
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    omega_schedule(p, iters, sp.omega);
+    sp.damping = p->pressure_damping;
+    {
+        volatile float dh = h->cfg.density * h->cfg.h;
+        sp.cp = dh / dt;                                   // fluid.go:158
+    }
+    CK(cudaMemsetAsync(h->d_red, 0, 32 * sizeof(unsigned), h->stream));
+    h->stats.sweeps_run = (int)iters;
+    h->stats.rolled_back = 0;
+    if (iters == 0) return FB_OK;
+
+    if (p->solver == FB_SOLVER_EXACT) {
+        if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "exact (lexicographic) solver is single-GPU only");
+        // The early exit of fluid.go:175 depends on a full sweep's max|div|, which a
+        // fused wavefront only knows afterwards: run optimistically from a backup
+        // and, if some sweep k < iters-1 met the tolerance, replay exactly k+1 sweeps.
+        float *bkU, *bkV, *bkP;
+        TRY(scratch(h, SCR_BKU, &bkU)); TRY(scratch(h, SCR_BKV, &bkV)); TRY(scratch(h, SCR_VIEW, &bkP));
+        TRY(copy_plane(h, bkU, h->f[FB_U])); TRY(copy_plane(h, bkV, h->f[FB_V])); TRY(copy_plane(h, bkP, h->f[FB_P]));
+        TRY(exact_sweeps(h, sp, 0, (int)iters));
+        TRY(read_stats(h, iters));
+        const float tolerance = 1e-5f;
+        int stop = -1;
+        for (unsigned k = 0; k + 1 < iters; k++) if (h->stats.max_div[k] < tolerance) { stop = (int)k; break; }
+        if (stop >= 0) {
+            TRY(copy_plane(h, h->f[FB_U], bkU)); TRY(copy_plane(h, h->f[FB_V], bkV)); TRY(copy_plane(h, h->f[FB_P], bkP));
+            CK(cudaMemsetAsync(h->d_red, 0, 32 * sizeof(unsigned), h->stream));
+            TRY(exact_sweeps(h, sp, 0, stop + 1));
+            TRY(read_stats(h, (unsigned)stop + 1));
+            h->stats.sweeps_run = stop + 1;
+            h->stats.rolled_back = 1;
+        }
+        return FB_OK;
+    }
+
+    // red-black, unfused reference path: one launch per half sweep
+    int ib, ie; range(h, h->cfg.ghost, ib, ie);
+    dim3 grid, block;
+    plane_launch(h->g, ib, ie, grid, block, h->g.NY / 2 + 1);
+    for (unsigned it = 0; it < iters; it++)
+        for (int colour = 0; colour < 2; colour++) {
+            k_redblack_half<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P], colour,
+                                                           sp.omega[it], sp.damping, sp.cp, h->d_red + it, ib, ie);
+            CKL("k_redblack_half");
+        }
+    return FB_OK;
+}
+
+// ---- the other phases ---------------------------------------------------------------
+static int clear_pressure(fb_handle *h)   // fluid.go:83
+{
+    CK(cudaMemsetAsync(h->f[FB_P], 0, h->plane_floats * sizeof(float), h->stream));
+    return FB_OK;
+}
+
+static int apply_viscosity(fb_handle *h, const fb_params *p, float dt)   // fluid.go:112-142
+{
+    if (!(p->viscosity_diffusion > 0.0f)) return FB_OK;
+    volatile float visc = p->viscosity_diffusion * dt;
+    TRY(copy_plane(h, h->f[FB_NEWU], h->f[FB_U]));
+    TRY(copy_plane(h, h->f[FB_NEWV], h->f[FB_V]));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_viscosity<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_NEWU], h->f[FB_NEWV], visc, ib, ie);
+    CKL("k_viscosity");
+    TRY(copy_plane(h, h->f[FB_U], h->f[FB_NEWU]));
+    TRY(copy_plane(h, h->f[FB_V], h->f[FB_NEWV]));
+    return FB_OK;
+}
+
+static int confinement(fb_handle *h, const fb_params *p, float dt)   // fluid.go:449-493
+{
+    float *curl;
+    TRY(scratch(h, SCR_CURL, &curl));
+    int ib, ie;
+    range(h, 1, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_curl<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], curl, h->cfg.h, ib, ie);
+    CKL("k_curl");
+    range(h, 0, ib, ie);
+    plane_launch(h->g, ib, ie, grid, block);
+    k_confine<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], curl, h->cfg.h, dt, p->confinement, ib, ie);
+    CKL("k_confine");
+    return FB_OK;
+}
+
+static int turbulence(fb_handle *h, const fb_params *p, float dt)   // fluid.go:496-526
+{
+    if (!(p->turbulence_strength > 0.0f)) return FB_OK;
+    float *nU, *nV;
+    TRY(scratch(h, SCR_NOISEU, &nU)); TRY(scratch(h, SCR_NOISEV, &nV));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    if (!h->noise_ready) {
+        k_noise_init<<<grid, block, 0, h->stream>>>(h->g, nU, nV, ib, ie);
+        CKL("k_noise_init");
+        h->noise_ready = true;
+    }
+    volatile float ts = p->turbulence_strength * dt;
+    k_turbulence<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], nU, nV, ts, ib, ie);
+    CKL("k_turbulence");
+    return FB_OK;
+}
+
+static int handle_borders(fb_handle *h)   // fluid.go:236-289
+{
+    int ib, ie; range(h, 0, ib, ie);
+    const int n = (ie - ib) + 2 * h->g.NY;
+    k_handle_borders<<<cdiv(n, 256), 256, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], ib, ie);
+    CKL("k_handle_borders");
+    return FB_OK;
+}
+
+static int advect_velocity(fb_handle *h, float dt)   // fluid.go:291-333
+{
+    TRY(copy_border(h, h->f[FB_NEWU], h->f[FB_U]));
+    TRY(copy_border(h, h->f[FB_NEWV], h->f[FB_V]));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_trace_velocity<false><<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_U], h->f[FB_V],
+                                                           h->f[FB_NEWU], h->f[FB_NEWV], dt, h->cfg.h, ib, ie, h->d_bad);
+    CKL("k_trace_velocity");
+    TRY(copy_plane(h, h->f[FB_U], h->f[FB_NEWU]));   // copy(f.U, f.newU), fluid.go:331 (Q-6)
+    TRY(copy_plane(h, h->f[FB_V], h->f[FB_NEWV]));
+    return FB_OK;
+}
+
+static int advect_smoke(fb_handle *h, const fb_params *p, float dt)   // fluid.go:400-434
+{
+    TRY(copy_border(h, h->f[FB_NEWM], h->f[FB_M]));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_trace_smoke<false><<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_M], h->f[FB_M],
+                                                        h->f[FB_NEWM], dt, h->cfg.h, p->smoke_advection,
+                                                        p->viscosity_diffusion, ib, ie, h->d_bad);
+    CKL("k_trace_smoke");
+    TRY(copy_plane(h, h->f[FB_M], h->f[FB_NEWM]));
+    return FB_OK;
+}
+
+static int advect_velocity_bfecc(fb_handle *h, float dt)   // fluid.go:911-994 (Q-10)
+{
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "BFECC needs halo exchanges between its passes; drive it per pass from the host layer");
+    float *origU, *origV, *fwdU, *fwdV, *bwdU, *bwdV;
+    TRY(scratch(h, SCR_A, &origU)); TRY(scratch(h, SCR_B, &origV));
+    TRY(scratch(h, SCR_C, &fwdU)); TRY(scratch(h, SCR_D, &fwdV));
+    TRY(scratch(h, SCR_E, &bwdU)); TRY(scratch(h, SCR_F, &bwdV));
+    TRY(copy_plane(h, origU, h->f[FB_U])); TRY(copy_plane(h, origV, h->f[FB_V]));
+    TRY(advect_velocity(h, dt));
+    TRY(copy_plane(h, fwdU, h->f[FB_U])); TRY(copy_plane(h, fwdV, h->f[FB_V]));
+    TRY(copy_plane(h, h->f[FB_U], origU)); TRY(copy_plane(h, h->f[FB_V], origV));
+    CK(cudaMemsetAsync(bwdU, 0, h->plane_floats * sizeof(float), h->stream));
+    CK(cudaMemsetAsync(bwdV, 0, h->plane_floats * sizeof(float), h->stream));
+    TRY(copy_border(h, bwdU, fwdU)); TRY(copy_border(h, bwdV, fwdV));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_trace_velocity<true><<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], fwdU, fwdV, bwdU, bwdV,
+                                                          dt, h->cfg.h, ib, ie, h->d_bad);
+    CKL("k_trace_velocity<back>");
+    // corrected field goes straight into U,V (copy(f.U, corrU), fluid.go:991)
+    k_bfecc_correct<false><<<grid, block, 0, h->stream>>>(h->g, origU, bwdU, h->f[FB_U], ib, ie);
+    CKL("k_bfecc_correct");
+    k_bfecc_correct<false><<<grid, block, 0, h->stream>>>(h->g, origV, bwdV, h->f[FB_V], ib, ie);
+    CKL("k_bfecc_correct");
+    TRY(advect_velocity(h, dt));
+    return FB_OK;
+}
+
+static int advect_smoke_bfecc(fb_handle *h, const fb_params *p, float dt)   // fluid.go:997-1051 (Q-11)
+{
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "BFECC needs halo exchanges between its passes; drive it per pass from the host layer");
+    float *origM, *fwdM, *bwdM;
+    TRY(scratch(h, SCR_A, &origM)); TRY(scratch(h, SCR_C, &fwdM)); TRY(scratch(h, SCR_E, &bwdM));
+    TRY(copy_plane(h, origM, h->f[FB_M]));
+    TRY(advect_smoke(h, p, dt));
+    TRY(copy_plane(h, fwdM, h->f[FB_M]));
+    CK(cudaMemsetAsync(bwdM, 0, h->plane_floats * sizeof(float), h->stream));
+    TRY(copy_border(h, bwdM, fwdM));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_trace_smoke<true><<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_M], fwdM, bwdM, dt,
+                                                       h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    CKL("k_trace_smoke<back>");
+    k_bfecc_correct<true><<<grid, block, 0, h->stream>>>(h->g, origM, bwdM, h->f[FB_M], ib, ie);
+    CKL("k_bfecc_correct<nonneg>");
+    TRY(advect_smoke(h, p, dt));
+    return FB_OK;
+}
+
+// ---- edits ----------------------------------------------------------------------------
+static EditFields edit_fields(fb_handle *h)
+{
+    EditFields f;
+    f.U = h->f[FB_U]; f.V = h->f[FB_V]; f.nU = h->f[FB_NEWU]; f.nV = h->f[FB_NEWV];
+    f.P = h->f[FB_P]; f.S = h->f[FB_S]; f.M = h->f[FB_M]; f.nM = h->f[FB_NEWM];
+    return f;
+}
+
+static long long cmd_cells(const Grid &g, const fb_edit_cmd &c)
+{
+    if (c.op == FB_EDIT_CIRCLE_OBSTACLE) return (long long)(2 * c.i1 + 1) * (2 * c.i1 + 1);
+    if (c.op == FB_EDIT_RESET) return (long long)g.NX * g.NY;
+    long long ni = (long long)c.i1 - c.i0, nj = (long long)c.j1 - c.j0;
+    return ni > 0 && nj > 0 ? ni * nj : 0;
+}
+
+static int validate_cmd(fb_handle *h, const fb_edit_cmd &c)
+{
+    const Grid &g = h->g;
+    switch (c.op) {
+    case FB_EDIT_SET_SOLID: case FB_EDIT_SET_VELOCITY: case FB_EDIT_ADD_SMOKE: case FB_EDIT_SET_SMOKE:
+    case FB_EDIT_SET_VELOCITY_IF_FLUID: case FB_EDIT_ADD_SMOKE_IF_FLUID:
+        // the reference panics on out-of-range indices (walls.go:6-11, 63-68, 75-80)
+        if (c.i0 < 0 || c.j0 < 0 || c.i1 > g.NX || c.j1 > g.NY || c.i1 < c.i0 || c.j1 < c.j0)
+            return fail(h, FB_ERR_INVALID, "edit rectangle out of range");
+        return FB_OK;
+    case FB_EDIT_APPLY_FORCE:      // silently ignores ring / out of range (fluid.go:762-764)
+    case FB_EDIT_RESET:
+        return FB_OK;
+    case FB_EDIT_CIRCLE_OBSTACLE:  // clips to the domain (fluid.go:897-899)
+        if (c.i1 < 0) return fail(h, FB_ERR_INVALID, "negative radius");
+        return FB_OK;
+    default:
+        return fail(h, FB_ERR_INVALID, "unknown edit op");
+    }
+}
+
+// `staged`: the list already sits in h->d_cmds (fb_step stages its per-step list once)
+static int run_edits(fb_handle *h, const fb_edit_cmd *cmds, size_t n, bool validate, bool staged = false)
+{
+    if (n == 0) return FB_OK;
+    if (!cmds) return FB_ERR_INVALID;
+    if (validate) for (size_t q = 0; q < n; q++) TRY(validate_cmd(h, cmds[q]));
+    if (!staged) {
+        if (n > h->d_cmds_cap) {
+            if (h->d_cmds) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_cmds)); h->d_cmds = nullptr; }
+            size_t cap = n < 1024 ? 1024 : n * 2;
+            CK(cudaMalloc(&h->d_cmds, cap * sizeof(fb_edit_cmd)));
+            h->d_cmds_cap = cap;
+        }
+        // the staging copy must finish before the caller's buffer may change
+        CK(cudaMemcpyAsync(h->d_cmds, cmds, n * sizeof(fb_edit_cmd), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    const EditFields f = edit_fields(h);
+    const long long SMALL = 1 << 14;
+    size_t q = 0;
+    while (q < n) {
+        if (cmd_cells(h->g, cmds[q]) > SMALL) {
+            const fb_edit_cmd &c = cmds[q];
+            int nj = c.op == FB_EDIT_CIRCLE_OBSTACLE ? 2 * c.i1 + 1 : (c.op == FB_EDIT_RESET ? h->g.NY : c.j1 - c.j0);
+            int ni = c.op == FB_EDIT_CIRCLE_OBSTACLE ? 2 * c.i1 + 1 : (c.op == FB_EDIT_RESET ? h->g.NX : c.i1 - c.i0);
+            dim3 grid(cdiv(nj, 256), ni < 4096 ? ni : 4096, 1);
+            k_edit_one<<<grid, 256, 0, h->stream>>>(h->g, f, c);
+            CKL("k_edit_one");
+            q++;
+        } else {
+            size_t e = q;
+            while (e < n && cmd_cells(h->g, cmds[e]) <= SMALL) e++;
+            k_edits_seq<<<1, 1024, 0, h->stream>>>(h->g, f, h->d_cmds + q, (int)(e - q));
+            CKL("k_edits_seq");
+            q = e;
+        }
+    }
+    return FB_OK;
+}
+
+extern "C" int fb_edit(fb_handle *h, const fb_edit_cmd *cmds, size_t n)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    return run_edits(h, cmds, n, true);
+}
+
+extern "C" int fb_apply_force_radius(fb_handle *h, int32_t cx, int32_t cy, float fx, float fy, int32_t radius)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    std::vector<fb_edit_cmd> cmds;
+    auto push = [&](int i, int j, float ax, float ay) {
+        fb_edit_cmd c; c.op = FB_EDIT_APPLY_FORCE; c.i0 = i; c.j0 = j; c.i1 = i + 1; c.j1 = j + 1; c.a = ax; c.b = ay;
+        cmds.push_back(c);
+    };
+    if (radius <= 0) {
+        push(cx, cy, fx, fy);                              // fluid.go:775-778
+    } else {
+        const float r2 = (float)((long long)radius * radius);
+        for (int i = cx - radius; i <= cx + radius; i++)
+            for (int j = cy - radius; j <= cy + radius; j++) {
+                if (i < 1 || i >= h->g.NX - 1 || j < 1 || j >= h->g.NY - 1) continue;
+                volatile float dx = (float)(i - cx), dy = (float)(j - cy);
+                volatile float dx2 = dx * dx, dy2 = dy * dy;
+                volatile float dist2 = dx2 + dy2;
+                if (dist2 > r2) continue;
+                volatile float num = -3.0f * dist2;
+                volatile float arg = num / r2;
+                const float weight = (float)exp((double)arg);   // fluid.go:792
+                volatile float wx = fx * weight, wy = fy * weight;
+                push(i, j, wx, wy);
+            }
+    }
+    return run_edits(h, cmds.data(), cmds.size(), false);
+}
+
+// ---- the step -------------------------------------------------------------------------
+static int check_params(fb_handle *h, const fb_params *p)
+{
+    if (!p) return fail(h, FB_ERR_INVALID, "null params");
+    if (p->solver != FB_SOLVER_EXACT && p->solver != FB_SOLVER_REDBLACK) return fail(h, FB_ERR_INVALID, "unknown solver");
+    if (p->iters < 0 || p->iters > 32) return fail(h, FB_ERR_INVALID, "iters out of range");
+    return FB_OK;
+}
+
+extern "C" int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nsteps,
+                       const fb_edit_cmd *per_step, size_t n_per_step)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    TRY(check_params(h, p));
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "fb_step is single-rank; with nranks > 1 the host layer sequences fb_phase calls and halo exchanges");
+    if (n_per_step) for (size_t q = 0; q < n_per_step; q++) TRY(validate_cmd(h, per_step[q]));
+    const unsigned iters = p->iters > 0 ? (unsigned)p->iters : 8u;
+    for (int s = 0; s < nsteps; s++) {
+        TRY(run_edits(h, per_step, n_per_step, false, s > 0));
+        TRY(clear_pressure(h));                                   // fluid.go:83
+        if (p->viscosity_diffusion > 0.0f) TRY(apply_viscosity(h, p, dt));   // fluid.go:86-88
+        TRY(make_incompressible(h, p, dt, iters));                // fluid.go:90
+        if (p->confinement != 0.0f) TRY(confinement(h, p, dt));   // fluid.go:92-94
+        if (p->turbulence_strength > 0.0f) TRY(turbulence(h, p, dt));   // fluid.go:97-99
+        TRY(handle_borders(h));                                   // fluid.go:101
+        if (p->use_bfecc) {                                       // fluid.go:102-108
+            TRY(advect_velocity_bfecc(h, dt));
+            TRY(advect_smoke_bfecc(h, p, dt));
+        } else {
+            TRY(advect_velocity(h, dt));
+            TRY(advect_smoke(h, p, dt));
+        }
+    }
+    return FB_OK;
+}
+
+extern "C" int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float dt, uint32_t iters)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    TRY(check_params(h, p));
+    switch (phase) {
+    case FB_PHASE_MAKE_INCOMPRESSIBLE: return make_incompressible(h, p, dt, iters);
+    case FB_PHASE_ADVECT_VELOCITY: TRY(advect_velocity(h, dt)); return check_bad(h);
+    case FB_PHASE_ADVECT_SMOKE: TRY(advect_smoke(h, p, dt)); return check_bad(h);
+    case FB_PHASE_HANDLE_BORDERS: return handle_borders(h);
+    case FB_PHASE_CONFINEMENT: return confinement(h, p, dt);
+    case FB_PHASE_TURBULENCE: return turbulence(h, p, dt);
+    case FB_PHASE_ADVECT_VELOCITY_BFECC: return advect_velocity_bfecc(h, dt);
+    case FB_PHASE_ADVECT_SMOKE_BFECC: return advect_smoke_bfecc(h, p, dt);
+    case FB_PHASE_VISCOSITY: return apply_viscosity(h, p, dt);
+    case FB_PHASE_CLEAR_PRESSURE: return clear_pressure(h);
+    default: return fail(h, FB_ERR_INVALID, "unknown phase");
+    }
+}
+
+extern "C" int fb_get_solve_stats(fb_handle *h, fb_solve_stats *out)
+{
+    if (!h || !out) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (h->stats.rolled_back == 0) TRY(read_stats(h, (unsigned)h->stats.sweeps_run));
+    *out = h->stats;
+    return FB_OK;
+}
+
+// ---- transfers ------------------------------------------------------------------------
+static float *field_ptr(fb_handle *h, int field) { return (field >= 0 && field < FB_NFIELDS) ? h->f[field] : nullptr; }
+
+extern "C" int fb_upload(fb_handle *h, int32_t field, const float *host)
+{
+    if (!h || !host) return FB_ERR_INVALID;
+    float *d = field_ptr(h, field);
+    if (!d) return fail(h, FB_ERR_INVALID, "bad field");
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    // all lines this rank holds (owned + ghosts) are taken from the global array
+    const float *src = host + (size_t)g.i_alloc0 * g.NY;
+    CK(cudaMemcpy2DAsync(d, (size_t)g.pitch * 4, src, (size_t)g.NY * 4, (size_t)g.NY * 4, (size_t)g.lines_alloc,
+                         cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FB_OK;
+}
+
+extern "C" int fb_download(fb_handle *h, int32_t field, float *host)
+{
+    if (!h || !host) return FB_ERR_INVALID;
+    float *d = field_ptr(h, field);
+    if (!d) return fail(h, FB_ERR_INVALID, "bad field");
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    float *dst = host + (size_t)g.i_lo * g.NY;
+    CK(cudaMemcpy2DAsync(dst, (size_t)g.NY * 4, d + g.at(g.i_lo, 0), (size_t)g.pitch * 4, (size_t)g.NY * 4,
+                         (size_t)(g.i_hi - g.i_lo), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FB_OK;
+}
+
+extern "C" int fb_host_mirror(fb_handle *h, int32_t field, float **ptr, size_t *count)
+{
+    if (!h || !ptr) return FB_ERR_INVALID;
+    if (field < 0 || field >= FB_NFIELDS) return fail(h, FB_ERR_INVALID, "bad field");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->g.NX * h->g.NY;
+    if (!h->mirror[field]) {
+        CK(cudaMallocHost(&h->mirror[field], n * sizeof(float)));
+        memset(h->mirror[field], 0, n * sizeof(float));
+    }
+    *ptr = h->mirror[field];
+    if (count) *count = n;
+    return FB_OK;
+}
+
+// ---- views and reductions ---------------------------------------------------------------
+static float key2f(unsigned k)
+{
+    unsigned b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    float f; memcpy(&f, &b, 4);
+    return f;
+}
+
+static unsigned f2key_host(float f)
+{
+    unsigned b; memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+extern "C" int fb_view(fb_handle *h, int32_t kind, float *out, float *min_value, float *max_value)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    // sentinels of pressure.go:6-7 / fluid.go:810-811
+    unsigned init[2] = { f2key_host(3.402823466e+38f), f2key_host(-3.402823466e+38f) };
+    CK(cudaMemcpyAsync(h->d_red + 32, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    const float *src = nullptr;
+    switch (kind) {
+    case FB_VIEW_SMOKE: src = h->f[FB_M]; break;
+    case FB_VIEW_PRESSURE: src = h->f[FB_P]; break;
+    case FB_VIEW_VELOCITY_MAGNITUDE: case FB_VIEW_VORTICITY: {
+        float *view;
+        TRY(scratch(h, SCR_VIEW, &view));
+        if (kind == FB_VIEW_VORTICITY)
+            k_view<FB_VIEW_VORTICITY><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        else
+            k_view<FB_VIEW_VELOCITY_MAGNITUDE><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        CKL("k_view");
+        src = view;
+        break;
+    }
+    default: return fail(h, FB_ERR_INVALID, "unknown view");
+    }
+    if (kind == FB_VIEW_SMOKE || kind == FB_VIEW_PRESSURE) {
+        k_minmax_all<<<grid, block, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
+        CKL("k_minmax_all");
+    }
+    CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    if (out) {
+        float *dst = out + (size_t)g.i_lo * g.NY;
+        CK(cudaMemcpy2DAsync(dst, (size_t)g.NY * 4, src + g.at(g.i_lo, 0), (size_t)g.pitch * 4, (size_t)g.NY * 4,
+                             (size_t)(g.i_hi - g.i_lo), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (min_value) *min_value = key2f(h->h_red[32]);
+    if (max_value) *max_value = key2f(h->h_red[33]);
+    return FB_OK;
+}
+
+extern "C" int fb_reduce(fb_handle *h, int32_t kind, float *out)
+{
+    if (!h || !out) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    CK(cudaMemsetAsync(h->d_red + 40, 0, sizeof(unsigned), h->stream));
+    if (kind == FB_REDUCE_MAX_DIVERGENCE)
+        k_reduce_max<FB_REDUCE_MAX_DIVERGENCE><<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->d_red + 40, ib, ie);
+    else if (kind == FB_REDUCE_MAX_ABS_VELOCITY)
+        k_reduce_max<FB_REDUCE_MAX_ABS_VELOCITY><<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->d_red + 40, ib, ie);
+    else return fail(h, FB_ERR_INVALID, "unknown reduction");
+    CKL("k_reduce_max");
+    CK(cudaMemcpyAsync(h->h_red + 40, h->d_red + 40, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_red + 40, 4);
+    return FB_OK;
+}
+
+extern "C" int fb_sample_velocity(fb_handle *h, size_t n, const float *xy, float *uv)
+{
+    if (!h || (n && (!xy || !uv))) return FB_ERR_INVALID;
+    if (n == 0) return FB_OK;
+    CK(cudaSetDevice(h->device));
+    float *dxy = nullptr, *duv = nullptr;
+    CK(cudaMalloc(&dxy, n * 2 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&duv, n * 2 * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(dxy); return fail(h, FB_ERR_CUDA, "cudaMalloc", e); }
+    int rc = FB_OK;
+    do {
+        if ((e = cudaMemcpyAsync(dxy, xy, n * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+        k_sample_velocity<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], dxy, duv, n, h->cfg.h, h->d_bad);
+        h->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(uv, duv, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(h->stream);
+    } while (0);
+    if (e != cudaSuccess) rc = fail(h, FB_ERR_CUDA, "fb_sample_velocity", e);
+    cudaFree(dxy); cudaFree(duv);
+    return rc;
+}
+
+// ---- halo regions -----------------------------------------------------------------------
+extern "C" int fb_halo_region(fb_handle *h, int32_t field, int32_t side, int32_t lines,
+                              void **send_ptr, void **recv_ptr, size_t *bytes)
+{
+    if (!h) return FB_ERR_INVALID;
+    float *d = field_ptr(h, field);
+    if (!d) return fail(h, FB_ERR_INVALID, "bad field");
+    const Grid &g = h->g;
+    if (lines < 1 || lines > h->cfg.ghost) return fail(h, FB_ERR_INVALID, "halo wider than the ghost zone");
+    if (lines > g.i_hi - g.i_lo) return fail(h, FB_ERR_INVALID, "halo wider than the slab");
+    int send_i, recv_i;
+    if (side == 0) { send_i = g.i_lo; recv_i = g.i_lo - lines; }
+    else if (side == 1) { send_i = g.i_hi - lines; recv_i = g.i_hi; }
+    else return fail(h, FB_ERR_INVALID, "side must be 0 or 1");
+    if (recv_i < g.i_alloc0 || recv_i + lines > g.i_alloc0 + g.lines_alloc)
+        return fail(h, FB_ERR_INVALID, "no neighbour on that side");
+    if (send_ptr) *send_ptr = d + g.at(send_i, 0);
+    if (recv_ptr) *recv_ptr = d + g.at(recv_i, 0);
+    if (bytes) *bytes = (size_t)lines * g.pitch * sizeof(float);
+    return FB_OK;
+}

@@ -1,0 +1,197 @@
+/*
+ * fluidb200.h -- C ABI of libfluidb200.so: the B200 (sm_100a) implementation of
+ * the per-step hot path of TheFellow/fluid's Go package pkg/fluid.
+ *
+ * This is the drop-in boundary: a cgo (or ctypes) binding of these entry points
+ * backs the exported Go API of pkg/fluid.  Plain pointers
+ * and sizes only; no C++/torch types.  Every call returns FB_OK (0) or a
+ * negative fb_status, never throws, never aborts.  A handle is not thread-safe;
+ * every entry point selects the handle's CUDA device itself, so calls may come
+ * from any OS thread (Go moves goroutines between threads).
+ *
+ * Citations are file:line relative to the reference checkout.
+ *
+ * Grid: NumX = width+2, NumY = height+2 (pkg/fluid/fluid.go:42-50); host-side
+ * arrays are dense row-major [NumX][NumY] float32 with index i*NumY+j exactly
+ * as the reference's slices (fluid.go:189).  The device layout is private
+ * (padded pitch).
+ */
+#ifndef FLUIDB200_H
+#define FLUIDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_handle fb_handle;
+
+typedef enum fb_status {
+    FB_OK = 0,
+    FB_ERR_INVALID = -1,     /* bad argument (the reference panics: walls.go:6-11) */
+    FB_ERR_CUDA = -2,        /* CUDA runtime error; see fb_last_error */
+    FB_ERR_NOMEM = -3,
+    FB_ERR_UNSUPPORTED = -4, /* e.g. exact solver with nranks > 1 */
+    FB_ERR_HALO = -5         /* a semi-Lagrangian trace left the ghost zone */
+} fb_status;
+
+/* Persistent arrays of `type Fluid` (fluid.go:17-23). */
+typedef enum fb_field {
+    FB_U = 0, FB_V = 1, FB_NEWU = 2, FB_NEWV = 3,
+    FB_P = 4, FB_S = 5, FB_M = 6, FB_NEWM = 7,
+    FB_NFIELDS = 8
+} fb_field;
+
+/* Pressure solver used by makeIncompressible (fluid.go:144-234). */
+typedef enum fb_solver {
+    /* Lexicographic in-place Gauss-Seidel/SOR, reproduced bit for bit by a
+     * skewed-tile wavefront (i + j + 2*sweep ordering).  Single GPU only. */
+    FB_SOLVER_EXACT = 0,
+    /* Same per-cell update in red-black order, all iterations fused in one pass.
+     * Order-independent, slab-decomposable; reaches the reference's residual. */
+    FB_SOLVER_REDBLACK = 1
+} fb_solver;
+
+/* fb_create arguments; replaces fluid.New(density, width, height, h) (fluid.go:42). */
+typedef struct fb_config {
+    int32_t width, height;   /* GLOBAL interior size */
+    float density, h;
+    int32_t device;          /* CUDA device ordinal */
+    int32_t rank, nranks;    /* row-slab decomposition over i; 0,1 = single GPU */
+    int32_t ghost;           /* ghost lines per side when nranks > 1 (0 = default) */
+} fb_config;
+
+/* The exported knobs of `type Fluid` (fluid.go:25-39), package var Relaxation
+ * (fluid.go:7-9) and numIters (fluid.go:81).  Passed by value with every step
+ * because Go callers mutate the struct fields directly (main/main.go:271-278). */
+typedef struct fb_params {
+    float relaxation;            /* 1.9 */
+    float confinement;           /* 0 */
+    float viscosity_diffusion;   /* 0 */
+    float pressure_damping;      /* 1 */
+    float turbulence_strength;   /* 0.02 */
+    float smoke_advection;       /* 1 */
+    int32_t use_multigrid;       /* false; true is FB_ERR_UNSUPPORTED (out of scope) */
+    int32_t multigrid_levels;    /* 2 */
+    int32_t use_bfecc;           /* false */
+    int32_t solver;              /* fb_solver */
+    int32_t iters;               /* numIters; 0 = 8 (fluid.go:81) */
+} fb_params;
+
+/* Edit commands: the point edits of walls.go:5-93 and fluid.go:761-771,
+ * 894-907 generalised to half-open rectangles [i0,i1) x [j0,j1) so that presets
+ * on 16384^2 grids do not need 10^8 calls.  Commands apply in list order. */
+typedef enum fb_edit_op {
+    FB_EDIT_SET_SOLID = 0,      /* a != 0 -> solid; zeroes 4 faces in U,V,newU,newV (walls.go:19-48) */
+    FB_EDIT_SET_VELOCITY = 1,   /* U=a, V=b (walls.go:62-72) */
+    FB_EDIT_ADD_SMOKE = 2,      /* M += a (walls.go:74-83) */
+    FB_EDIT_APPLY_FORCE = 3,    /* U+=a, V+=b unless ring or solid (fluid.go:761-771) */
+    FB_EDIT_CIRCLE_OBSTACLE = 4,/* centre (i0,j0), radius i1 (fluid.go:894-907) */
+    FB_EDIT_RESET = 5,          /* walls.go:85-93: zero all but S */
+    FB_EDIT_SET_VELOCITY_IF_FLUID = 6, /* main/main.go:475-477 source guard */
+    FB_EDIT_ADD_SMOKE_IF_FLUID = 7,
+    FB_EDIT_SET_SMOKE = 8       /* M = a (fluid_bench_test.go:39 writes M directly) */
+} fb_edit_op;
+
+typedef struct fb_edit_cmd {
+    int32_t op;
+    int32_t i0, j0, i1, j1;
+    float a, b;
+} fb_edit_cmd;
+
+/* Single phases of Simulate, for the reference's white-box tests
+ * (fluid_test.go:56,117,179,239,310,332,1068-1083) and per-kernel parity. */
+typedef enum fb_phase_id {
+    FB_PHASE_MAKE_INCOMPRESSIBLE = 0,  /* fluid.go:144; uses `iters` */
+    FB_PHASE_ADVECT_VELOCITY = 1,      /* fluid.go:291 */
+    FB_PHASE_ADVECT_SMOKE = 2,         /* fluid.go:400 */
+    FB_PHASE_HANDLE_BORDERS = 3,       /* fluid.go:236 */
+    FB_PHASE_CONFINEMENT = 4,          /* fluid.go:449 */
+    FB_PHASE_TURBULENCE = 5,           /* fluid.go:496 */
+    FB_PHASE_ADVECT_VELOCITY_BFECC = 6,/* fluid.go:911 */
+    FB_PHASE_ADVECT_SMOKE_BFECC = 7,   /* fluid.go:997 */
+    FB_PHASE_VISCOSITY = 8,            /* fluid.go:112 */
+    FB_PHASE_CLEAR_PRESSURE = 9        /* fluid.go:83 */
+} fb_phase_id;
+
+typedef enum fb_view_kind {
+    FB_VIEW_SMOKE = 0,              /* smoke.go:5 */
+    FB_VIEW_PRESSURE = 1,           /* pressure.go:5 */
+    FB_VIEW_VELOCITY_MAGNITUDE = 2, /* fluid.go:841 */
+    FB_VIEW_VORTICITY = 3           /* fluid.go:806 */
+} fb_view_kind;
+
+typedef enum fb_reduce_kind {
+    FB_REDUCE_MAX_DIVERGENCE = 0,   /* fluid.go:876 */
+    FB_REDUCE_MAX_ABS_VELOCITY = 1  /* max(|U|+|V|) of fluid.go:534-543 */
+} fb_reduce_kind;
+
+typedef struct fb_solve_stats {
+    int32_t sweeps_run;       /* sweeps executed by the last solve (early exit, fluid.go:175) */
+    int32_t rolled_back;      /* exact solver: 1 if the early exit forced a re-run */
+    float max_div[32];        /* max pre-update |div| seen in each sweep (fluid.go:209-216) */
+} fb_solve_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int fb_create(const fb_config *cfg, fb_handle **out);          /* fluid.New, fluid.go:42 */
+int fb_destroy(fb_handle *h);
+const char *fb_last_error(const fb_handle *h);                 /* NUL-terminated, owned by h */
+int fb_default_params(fb_params *p);                           /* fluid.go:59-66, 7-9 */
+int fb_dims(const fb_handle *h, int64_t *num_x, int64_t *num_y,
+            int64_t *i_lo, int64_t *i_hi);                     /* global dims + owned slab */
+
+/* ---- the hot path ------------------------------------------------------- */
+/* (*Fluid).Simulate(dt) x nsteps (fluid.go:79-109).  `per_step` (may be NULL)
+ * is replayed before every step: the jet / source / sink re-imposition that
+ * main/main.go:233-241,474-486 performs before each Simulate. */
+int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nsteps,
+            const fb_edit_cmd *per_step, size_t n_per_step);
+int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float dt, uint32_t iters);
+int fb_get_solve_stats(fb_handle *h, fb_solve_stats *out);
+
+/* ---- edits (walls.go, fluid.go:761-796, 894-907) ------------------------ */
+int fb_edit(fb_handle *h, const fb_edit_cmd *cmds, size_t n);
+/* ApplyForceRadius (fluid.go:774-796): Gaussian weights exp(-3 d^2/r^2) are
+ * evaluated on the host in double precision like the reference. */
+int fb_apply_force_radius(fb_handle *h, int32_t cx, int32_t cy, float fx, float fy, int32_t radius);
+
+/* ---- field transfer (dense [NumX_global][NumY] host arrays) ------------- */
+/* Copies this rank's owned lines (all lines when nranks == 1).  `host` points at
+ * the start of the dense GLOBAL array. */
+int fb_upload(fb_handle *h, int32_t field, const float *host);
+int fb_download(fb_handle *h, int32_t field, float *host);
+/* Pinned host mirror owned by the library, dense global layout; a Go binding
+ * wraps it with unsafe.Slice to back the exported U/V/S/M slices. */
+int fb_host_mirror(fb_handle *h, int32_t field, float **ptr, size_t *count);
+
+/* ---- views and reductions (Q-14 semantics) ------------------------------ */
+int fb_view(fb_handle *h, int32_t kind, float *out_or_null, float *min_value, float *max_value);
+int fb_reduce(fb_handle *h, int32_t kind, float *out);
+/* SampleVelocity (fluid.go:799-803) for n points; xy and uv are [n][2]. */
+int fb_sample_velocity(fb_handle *h, size_t n, const float *xy, float *uv);
+
+/* ---- slab halo exchange (nranks > 1) ------------------------------------ */
+/* Device pointers to the `lines` ghost lines to RECEIVE from side (0 = lower i,
+ * 1 = upper i) and to the owned lines to SEND to that side; each region is
+ * `lines` contiguous rows of `pitch` floats.  The transport (NCCL send/recv,
+ * peer copies) belongs to the host layer. */
+int fb_halo_region(fb_handle *h, int32_t field, int32_t side, int32_t lines,
+                   void **send_ptr, void **recv_ptr, size_t *bytes);
+int fb_ghost_lines(const fb_handle *h, int32_t *ghost);
+
+/* ---- plumbing ----------------------------------------------------------- */
+int fb_stream(fb_handle *h, void **cuda_stream);   /* the stream all work is queued on */
+int fb_synchronize(fb_handle *h);
+/* CUDA-event timing on the handle's stream. */
+int fb_timer_start(fb_handle *h);
+int fb_timer_stop(fb_handle *h, float *elapsed_ms);
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+int fb_launch_count(const fb_handle *h, uint64_t *count);
+int fb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDB200_H */

@@ -1,0 +1,41 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with `-m gpu`)")
+    config.addinivalue_line("markers", "slow: long-running CPU test")
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+def _make_oracle(density, width, height, h, **kw):
+    import oracle
+    return oracle.New(density, width, height, h, **kw)
+
+
+def _make_gpu(density, width, height, h, **kw):
+    import fluid_b200
+    kw.setdefault("compat", True)
+    return fluid_b200.New(density, width, height, h, **kw)
+
+
+@pytest.fixture(params=["oracle", pytest.param("gpu", marks=pytest.mark.gpu)])
+def impl(request):
+    """Factory with the signature of fluid.New.  'oracle' = CPU restatement,
+    'gpu' = fluid_b200 in white-box (compat) mode so that f.U[i, j] = x works
+    like the reference's in-package tests."""
+    f = _make_oracle if request.param == "oracle" else _make_gpu
+    f.kind = request.param
+    return f
