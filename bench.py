@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the pkg/fluid per-step hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--solver redblack|exact]
+    python bench.py --impl reference ...      # the CPU restatement of the Go reference on host cores
+
+One JSON line on stdout (rank 0).  A "step" is one (*Fluid).Simulate over the whole
+grid with the preset's per-frame edits (jet / sources) replayed first, exactly what
+main/main.go:233-245 does per frame.  metric = cell-steps/s, a cell-step being one grid
+cell (ring included: NumX*NumY per step) advanced by one Simulate.
+
+value     device-resident: inputs live in HBM, K steps timed with CUDA events on the
+          library's stream between barriers + synchronizes, max over ranks.
+e2e       the frame loop a user of the Go API runs: per step the edit commands go
+          host->device, Simulate runs, and the Smoke() view (field + min/max) comes
+          back device->host into pinned memory (main/main.go Update + Draw).
+roofline  dominant phase of the step (largest share of device time, measured with CUDA
+          events per phase inside the timed region) against the measured HBM peak.
+cpu_baseline  oracle/ (C restatement of the Go reference, all host threads) on a bounded
+          sample of the same preset.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# algorithmic HBM bytes per cell-step by phase
+BYTES = {"project": 24, "turbulence": 20, "confinement": 20, "advect_velocity": 20, "advect_smoke": 20,
+         "bfecc_velocity": 68, "bfecc_smoke": 64}
+
+WORKLOADS = {
+    # name: (preset, width, height, bfecc, confinement, BASELINE.json config it restates)
+    "karman4096": ("karman", 4096, 4096, True, 0.1, "configs[2]: Karman 4096^2, BFECC + vorticity confinement"),
+    "jet16384": ("jet", 16384, 16384, False, 0.0, "configs[3]: jet 16384^2 per GPU, plain semi-Lagrangian"),
+    "jet4096": ("jet", 4096, 4096, False, 0.0, "jet 4096^2, plain semi-Lagrangian"),
+    "cavity1024": ("cavity", 1024, 1024, True, 0.0, "configs[1]: lid-driven cavity 1024^2, BFECC (fits L2)"),
+    "jet300": ("jet", 300, 251, False, 0.0, "configs[0]: jet at the reference's default 300x251 grid"),
+    "karman1024": ("karman", 1024, 1024, True, 0.1, "Karman 1024^2 (CPU sample size)"),
+}
+
+
+def step_bytes(bfecc: bool, confinement: float, turbulence: bool = True) -> int:
+    b = BYTES["project"]
+    if confinement != 0.0 or turbulence:
+        b += 20                      # a6+a7 share one pass
+    b += (BYTES["bfecc_velocity"] + BYTES["bfecc_smoke"]) if bfecc else (BYTES["advect_velocity"] + BYTES["advect_smoke"])
+    return b
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_fluid(mod, preset, solver, **kw):
+    f = mod.New(preset.density, preset.width, preset.height, preset.h, solver=solver, **kw)
+    f.edit(preset.init)
+    f.UseBFECC = bool(preset.params.get("use_bfecc", False))
+    f.Confinement = float(preset.params.get("confinement", 0.0))
+    return f
+
+
+def build_preset(name, width, height, bfecc, confinement):
+    from fluid_b200 import presets
+    if name == "karman":
+        return presets.karman(width, height, bfecc=bfecc, confinement=confinement)
+    if name == "cavity":
+        return presets.cavity(width, height, bfecc=bfecc)
+    return presets.jet(width, height, bfecc=bfecc)
+
+
+def cpu_reference_run(workload, steps, warmup, sample_size=None):
+    """The C restatement of the Go reference (oracle/) on the host cores, all threads, on a
+    bounded sample of the workload: the same preset at a grid the CPU finishes in seconds
+    (per-cell work is size-independent: h and dt are not rescaled)."""
+    import oracle
+    pname, w, h, bfecc, conf, _ = WORKLOADS[workload]
+    if sample_size is None:
+        sample_size = (min(w, 1024), min(h, 1024))
+    sw, sh = sample_size
+    p = build_preset(pname, sw, sh, bfecc, conf)
+    f = make_fluid(oracle, p, oracle.SOLVER_EXACT)
+    f.step(p.dt, warmup, p.per_step)
+    t0 = time.perf_counter()
+    f.step(p.dt, steps, p.per_step)
+    dt = time.perf_counter() - t0
+    cells = f.NumX * f.NumY
+    return {"value": cells * steps / dt, "unit": "cell-steps/s", "cores": int(f.threads), "kind": "port",
+            "sample": f"{pname} preset {sw}x{sh} (+ring), bfecc={bfecc}, confinement={conf}, {steps} steps after "
+                      f"{warmup} warm-up, oracle/ C restatement of the Go reference (lexicographic solver), "
+                      f"{int(f.threads)} threads (GOMAXPROCS-equivalent), nproc={os.cpu_count()}",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="karman4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--solver", default="redblack", choices=["redblack", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the exact-solver and e2e legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local = dist_env()
+    pname, width, height, bfecc, conf, cfg_desc = WORKLOADS[args.workload]
+    bpc = step_bytes(bfecc, conf)
+
+    if args.impl == "reference":
+        # rank 0 alone runs the CPU implementation; other ranks exit without work
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(args.workload, args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": "cell-steps/s", "value": r["value"], "unit": "cell-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "restates": cfg_desc, "solver": "lexicographic (reference)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import fluid_b200
+    from fluid_b200 import _lib as L
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    solver = fluid_b200.SOLVER_REDBLACK if args.solver == "redblack" else fluid_b200.SOLVER_EXACT
+    preset = build_preset(pname, width, height, bfecc, conf)
+
+    # ---- N > 1: every rank runs the same per-GPU workload on its own device ("weak").
+    # The slab-decomposed path (halo exchange between ranks) is selected by the host layer
+    # when fluid_b200.parallel is available; see DESIGN.md "Multi-GPU".
+    parallel = None
+    if world > 1:
+        try:
+            from fluid_b200 import parallel as parallel   # noqa: PLC0414
+        except Exception:
+            parallel = None
+
+    if parallel is not None and world > 1:
+        sim = parallel.SlabFluid(preset, solver=solver, device=local, rank=rank, nranks=world, weak=True)
+        cells_total = sim.global_cells
+        parallelism = f"row-slabs x{world}, NCCL halo exchange"
+    else:
+        sim = make_fluid(fluid_b200, preset, solver, device=local)
+        cells_total = sim.NumX * sim.NumY * world
+        parallelism = "single GPU" if world == 1 else f"{world} independent replicas"
+
+    def run_steps(n):
+        sim.step(preset.dt, n, preset.per_step)
+
+    def timed(n):
+        barrier()
+        sim.timer_start()
+        run_steps(n)
+        ms = sim.timer_stop()
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    run_steps(args.warmup)
+    sim.profile(True)
+    sim.profile_read()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = sim.launch_count()
+    ms = timed(args.steps)
+    launches = sim.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else {}
+    phases = sim.profile_read()
+    sim.profile(False)
+    value = cells_total * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant phase and of the whole step
+    peak, peak_src = measured_peak()
+    cells_rank = cells_total // world
+    phase_alg_bytes = {"project": 24, "confinement": 20, "turbulence": 0 if conf != 0.0 else 20,
+                       "advect_velocity": 68 if bfecc else 20, "advect_smoke": 64 if bfecc else 20,
+                       "clear_pressure": 0, "edits": 0, "borders": 0, "viscosity": 0}
+    shares = {k: v[0] for k, v in phases.items() if v[1] > 0}
+    total_phase_ms = sum(shares.values()) or 1.0
+    dom = max(shares, key=shares.get) if shares else "project"
+    dom_ms = shares.get(dom, 0.0) / max(phases[dom][1], 1) if shares else 0.0
+    dom_bytes = phase_alg_bytes.get(dom, 0) * cells_rank
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    proj_ms = phases["project"][0] / max(phases["project"][1], 1)
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "alg_bytes_per_cell": phase_alg_bytes.get(dom, 0), "ms_per_launch": dom_ms,
+        "share_of_step": shares.get(dom, 0.0) / total_phase_ms,
+        "step": {"alg_bytes_per_cell_step": bpc, "achieved": bpc * cells_rank / (ms / args.steps * 1e-3) / 1e9,
+                 "frac": bpc * cells_rank / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "pressure_solve": {"alg_bytes_per_cell": 24, "ms": proj_ms,
+                           "achieved": 24 * cells_rank / (proj_ms * 1e-3) / 1e9 if proj_ms > 0 else 0.0,
+                           "frac": (24 * cells_rank / (proj_ms * 1e-3) / 1e9 / peak) if proj_ms > 0 else 0.0},
+        "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1] > 0},
+    }
+
+    # ---- e2e: the frame loop through the public API with host buffers
+    e2e = None
+    secondary = {}
+    if (not args.no_secondary) and (parallel is None or world == 1):
+        per = fluid_b200.edits.pack(preset.per_step)
+        h2d = int(per.nbytes)
+        mirror = sim._mirror(L.M)            # pinned host memory owned by the library
+        mn, mx = __import__("ctypes").c_float(), __import__("ctypes").c_float()
+        import ctypes as C
+
+        def frame():
+            sim.step(preset.dt, 1, per)      # edit commands host->device + Simulate
+            L.check(sim._h, L.lib.fb_view(sim._h, L.VIEW_SMOKE, mirror.ctypes.data, C.byref(mn), C.byref(mx)))
+
+        for _ in range(3):
+            frame()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": cells_total * args.steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(sim.NumX * sim.NumY * 4 + 8), "ms_per_step": e2e_s / args.steps * 1e3,
+               "what": "per step: edit commands H2D, Simulate, Smoke() view (field + min/max) D2H into pinned memory"}
+
+        # ---- the other solver on the same workload (reported, not the headline)
+        other = fluid_b200.SOLVER_EXACT if solver == fluid_b200.SOLVER_REDBLACK else fluid_b200.SOLVER_REDBLACK
+        sim.Solver = other
+        run_steps(2)
+        ms2 = timed(max(args.steps // 3, 3))
+        n2 = max(args.steps // 3, 3)
+        secondary = {"solver": "exact" if other == fluid_b200.SOLVER_EXACT else "redblack",
+                     "value": cells_total * n2 / (ms2 * 1e-3), "ms_per_step": ms2 / n2,
+                     "note": "exact = lexicographic wavefront, bit-identical to the reference restatement"}
+        sim.Solver = solver
+
+    # residual actually reached by the headline solver on the final state
+    st = sim.solve_stats() if hasattr(sim, "solve_stats") else {}
+    max_div_after = sim.MaxDivergence()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.workload, 8, 2)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "restates": cfg_desc, "grid_per_gpu": [width + 2, height + 2],
+                       "cells_total": cells_total, "preset": pname, "bfecc": bfecc, "confinement": conf,
+                       "turbulence": 0.02, "dt": preset.dt, "parallelism": parallelism,
+                       "solver": ("red-black SOR, 8 iterations fused, reference omega schedule with damped close"
+                                  if solver == fluid_b200.SOLVER_REDBLACK else
+                                  "lexicographic GS/SOR (bit-exact wavefront), 8 sweeps"),
+                       "l2": "working set >> 126 MB L2 (inputs larger than L2)" if cells_total // world > 8e6
+                             else "working set fits L2: HBM fraction not meaningful",
+                       "residual": {"max_div_after_last_step": max_div_after, "sweeps": st.get("sweeps_run")}},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk, "other_solver": secondary,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

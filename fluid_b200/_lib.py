@@ -25,6 +25,8 @@ SOLVER_EXACT, SOLVER_REDBLACK = 0, 1
 # fb_view_kind / fb_reduce_kind
 VIEW_SMOKE, VIEW_PRESSURE, VIEW_VELOCITY_MAGNITUDE, VIEW_VORTICITY = range(4)
 REDUCE_MAX_DIVERGENCE, REDUCE_MAX_ABS_VELOCITY = range(2)
+PROF_PHASES = ("edits", "clear_pressure", "viscosity", "project", "confinement", "turbulence", "borders",
+               "advect_velocity", "advect_smoke")
 
 
 class Config(C.Structure):
@@ -69,6 +71,8 @@ SYMBOLS = {
     "fb_synchronize": (C.c_int, [_H]),
     "fb_timer_start": (C.c_int, [_H]),
     "fb_timer_stop": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "fb_profile_enable": (C.c_int, [_H, C.c_int32]),
+    "fb_profile_read": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "fb_launch_count": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "fb_version": (C.c_int, []),
 }

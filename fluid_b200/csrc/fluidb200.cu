@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #define FB_VERSION 100
@@ -32,6 +33,9 @@ struct fb_handle {
     int *d_tile_counter; int *d_done; int epoch;
     fb_edit_cmd *d_cmds; size_t d_cmds_cap;
     cudaEvent_t ev0, ev1;
+    bool prof;
+    std::vector<cudaEvent_t> prof_pool;                 // recycled events
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pairs;
     uint64_t launches;
     fb_solve_stats stats;
     std::string err;
@@ -51,6 +55,28 @@ static int fail(fb_handle *h, int code, const char *what, cudaError_t e = cudaSu
 #define TRY(expr) do { int _s = (expr); if (_s != FB_OK) return _s; } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- per-phase event timing (fb_profile_*) ----------------------------------------
+struct ProfScope {
+    fb_handle *h; int phase; cudaEvent_t a, b; bool on;
+    static cudaEvent_t get(fb_handle *h) {
+        cudaEvent_t e = nullptr;
+        if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+        return e;
+    }
+    ProfScope(fb_handle *h_, int phase_) : h(h_), phase(phase_), a(nullptr), b(nullptr), on(h_->prof) {
+        if (!on) return;
+        a = get(h); b = get(h);
+        if (!a || !b) { on = false; return; }
+        cudaEventRecord(a, h->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(b, h->stream);
+        h->prof_pairs.push_back({phase, {a, b}});
+    }
+};
 
 static int scratch(fb_handle *h, int which, float **out)
 {
@@ -159,6 +185,8 @@ extern "C" int fb_destroy(fb_handle *h)
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
     if (h->d_done) cudaFree(h->d_done);
     if (h->d_cmds) cudaFree(h->d_cmds);
+    for (auto &pr : h->prof_pairs) { cudaEventDestroy(pr.second.first); cudaEventDestroy(pr.second.second); }
+    for (auto e : h->prof_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -210,6 +238,29 @@ extern "C" int fb_timer_stop(fb_handle *h, float *ms)
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return FB_OK;
+}
+
+extern "C" int fb_profile_enable(fb_handle *h, int32_t on)
+{
+    if (!h) return FB_ERR_INVALID;
+    h->prof = on != 0;
+    return FB_OK;
+}
+
+extern "C" int fb_profile_read(fb_handle *h, float *ms, int32_t *calls)
+{
+    if (!h || !ms || !calls) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < FB_PROF_NPHASES; k++) { ms[k] = 0.0f; calls[k] = 0; }
+    for (auto &pr : h->prof_pairs) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, pr.second.first, pr.second.second) == cudaSuccess) { ms[pr.first] += t; calls[pr.first]++; }
+        h->prof_pool.push_back(pr.second.first);
+        h->prof_pool.push_back(pr.second.second);
+    }
+    h->prof_pairs.clear();
     return FB_OK;
 }
 
@@ -270,6 +321,19 @@ static void omega_schedule(const fb_params *p, unsigned iters, float *omega)
         volatile float t = (initial - minRelax) * prog;
         omega[it] = initial - t;
     }
+}
+
+// Red-black schedule, one omega per HALF sweep (red, black, red, ...): the reference's
+// omega(iter) for every iteration but the last, which closes with a plain Gauss-Seidel
+// red half sweep (1.0) and a half-relaxed black one (0.5).  Red-black otherwise leaves
+// the entire residual on one colour; the damped close spreads it over both, which is
+// what brings max|div| down to the lexicographic solver's.
+static void omega_schedule_redblack(const fb_params *p, unsigned iters, float *omega)
+{
+    float per_iter[32];
+    omega_schedule(p, iters, per_iter);
+    for (unsigned it = 0; it < iters && it < 32; it++) omega[2 * it] = omega[2 * it + 1] = per_iter[it];
+    if (iters > 0) { omega[2 * iters - 2] = 1.0f; omega[2 * iters - 1] = 0.5f; }
 }
 
 static int ensure_order(fb_handle *h)
@@ -343,7 +407,8 @@ static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsig
     TRY(copy_border(h, h->f[FB_NEWV], h->f[FB_V]));
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
-    omega_schedule(p, iters, sp.omega);
+    if (p->solver == FB_SOLVER_EXACT) omega_schedule(p, iters, sp.omega);
+    else omega_schedule_redblack(p, iters, sp.omega);
     sp.damping = p->pressure_damping;
     {
         volatile float dh = h->cfg.density * h->cfg.h;
@@ -385,7 +450,7 @@ static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsig
     for (unsigned it = 0; it < iters; it++)
         for (int colour = 0; colour < 2; colour++) {
             k_redblack_half<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P], colour,
-                                                           sp.omega[it], sp.damping, sp.cp, h->d_red + it, ib, ie);
+                                                           sp.omega[2 * it + colour], sp.damping, sp.cp, h->d_red + it, ib, ie);
             CKL("k_redblack_half");
         }
     return FB_OK;
@@ -666,19 +731,19 @@ extern "C" int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nstep
     if (n_per_step) for (size_t q = 0; q < n_per_step; q++) TRY(validate_cmd(h, per_step[q]));
     const unsigned iters = p->iters > 0 ? (unsigned)p->iters : 8u;
     for (int s = 0; s < nsteps; s++) {
-        TRY(run_edits(h, per_step, n_per_step, false, s > 0));
-        TRY(clear_pressure(h));                                   // fluid.go:83
-        if (p->viscosity_diffusion > 0.0f) TRY(apply_viscosity(h, p, dt));   // fluid.go:86-88
-        TRY(make_incompressible(h, p, dt, iters));                // fluid.go:90
-        if (p->confinement != 0.0f) TRY(confinement(h, p, dt));   // fluid.go:92-94
-        if (p->turbulence_strength > 0.0f) TRY(turbulence(h, p, dt));   // fluid.go:97-99
-        TRY(handle_borders(h));                                   // fluid.go:101
-        if (p->use_bfecc) {                                       // fluid.go:102-108
-            TRY(advect_velocity_bfecc(h, dt));
-            TRY(advect_smoke_bfecc(h, p, dt));
+        { ProfScope ps(h, FB_PROF_EDITS); TRY(run_edits(h, per_step, n_per_step, false, s > 0)); }
+        { ProfScope ps(h, FB_PROF_CLEAR_PRESSURE); TRY(clear_pressure(h)); }               // fluid.go:83
+        if (p->viscosity_diffusion > 0.0f) { ProfScope ps(h, FB_PROF_VISCOSITY); TRY(apply_viscosity(h, p, dt)); }   // fluid.go:86-88
+        { ProfScope ps(h, FB_PROF_PROJECT); TRY(make_incompressible(h, p, dt, iters)); }   // fluid.go:90
+        if (p->confinement != 0.0f) { ProfScope ps(h, FB_PROF_CONFINEMENT); TRY(confinement(h, p, dt)); }   // fluid.go:92-94
+        if (p->turbulence_strength > 0.0f) { ProfScope ps(h, FB_PROF_TURBULENCE); TRY(turbulence(h, p, dt)); }   // fluid.go:97-99
+        { ProfScope ps(h, FB_PROF_BORDERS); TRY(handle_borders(h)); }                      // fluid.go:101
+        if (p->use_bfecc) {                                                                // fluid.go:102-108
+            { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_bfecc(h, dt)); }
+            { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc(h, p, dt)); }
         } else {
-            TRY(advect_velocity(h, dt));
-            TRY(advect_smoke(h, p, dt));
+            { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity(h, dt)); }
+            { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke(h, p, dt)); }
         }
     }
     return FB_OK;

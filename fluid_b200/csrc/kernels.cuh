@@ -27,7 +27,7 @@ struct Grid {
 };
 
 struct SolveParams {
-    float omega[32];   // per-sweep relaxation (fluid.go:169-170)
+    float omega[64];   // relaxation per sweep (exact) or per half sweep (red-black)
     float damping;     // PressureDamping (fluid.go:222)
     float cp;          // density*h/dt (fluid.go:158)
     int sweeps;        // sweeps fused in this launch

@@ -400,6 +400,16 @@ class Fluid:
         L.check(self._h, L.lib.fb_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def profile(self, on: bool = True):
+        L.check(self._h, L.lib.fb_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{phase: (ms_total, calls)} since the last read (CUDA events per phase)."""
+        n = len(L.PROF_PHASES)
+        ms, calls = (C.c_float * n)(), (C.c_int32 * n)()
+        L.check(self._h, L.lib.fb_profile_read(self._h, ms, calls))
+        return {name: (float(ms[k]), int(calls[k])) for k, name in enumerate(L.PROF_PHASES)}
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         L.check(self._h, L.lib.fb_launch_count(self._h, C.byref(n)))

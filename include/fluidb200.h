@@ -187,6 +187,17 @@ int fb_synchronize(fb_handle *h);
 /* CUDA-event timing on the handle's stream. */
 int fb_timer_start(fb_handle *h);
 int fb_timer_stop(fb_handle *h, float *elapsed_ms);
+/* Per-phase device time of fb_step, measured with CUDA events on the handle's
+ * stream around every phase (negligible cost; off by default).  fb_profile_read
+ * waits for the stream, adds up the pairs recorded since the last read into
+ * ms[FB_PROF_NPHASES] / calls[FB_PROF_NPHASES] and clears them. */
+typedef enum fb_prof_phase {
+    FB_PROF_EDITS = 0, FB_PROF_CLEAR_PRESSURE, FB_PROF_VISCOSITY, FB_PROF_PROJECT, FB_PROF_CONFINEMENT,
+    FB_PROF_TURBULENCE, FB_PROF_BORDERS, FB_PROF_ADVECT_VELOCITY, FB_PROF_ADVECT_SMOKE,
+    FB_PROF_NPHASES
+} fb_prof_phase;
+int fb_profile_enable(fb_handle *h, int32_t on);
+int fb_profile_read(fb_handle *h, float *ms, int32_t *calls);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int fb_launch_count(const fb_handle *h, uint64_t *count);
 int fb_version(void);

@@ -984,7 +984,8 @@ void fo_sample_velocity(const fo_fluid *f, float x, float y, float *u, float *v)
 /* ---- NOT in the reference: red-black ordering of the fluid.go:196-229 update.
  * One iteration = red half-sweep ((i+j) even) then black half-sweep; within a
  * half-sweep no two updated cells share a face, so the result is independent
- * of traversal order.  Omega schedule and copyBorder as fluid.go:144-186. */
+ * of traversal order.  copyBorder as fluid.go:145-146; omega per iteration as
+ * fluid.go:169-170 except for the closing iteration (see fo_project_redblack). */
 static float redblack_half(fo_fluid *f, float relaxation, float cp, int colour)
 {
     const int64_t n = f->NumY, NX = f->NumX, NY = f->NumY;
@@ -1015,25 +1016,38 @@ static float redblack_half(fo_fluid *f, float relaxation, float cp, int colour)
     return maxDiv;
 }
 
-float fo_project_redblack(fo_fluid *f, unsigned iters, float dt)
+float fo_project_redblack_sched(fo_fluid *f, const float *omega, unsigned iters, float dt)
 {
     fo_copy_border(f, f->newU, f->U);
     fo_copy_border(f, f->newV, f->V);
     float cp = f->density * f->h / dt;
-    const float minRelaxation = 1.2f;
     float maxDiv = 0.0f;
     f->last_iters = 0;
     for (unsigned iter = 0; iter < iters; iter++) {
-        float iterProgress = (float)iter / (float)iters;
-        float t = (f->Relaxation - minRelaxation) * iterProgress;
-        float omega = f->Relaxation - t;
-        float a = redblack_half(f, omega, cp, 0);
-        float b = redblack_half(f, omega, cp, 1);
+        float a = redblack_half(f, omega[2 * iter], cp, 0);
+        float b = redblack_half(f, omega[2 * iter + 1], cp, 1);
         maxDiv = a > b ? a : b;
         f->last_iters = (int)iter + 1;
         f->last_maxdiv = maxDiv;
     }
     return maxDiv;
+}
+
+float fo_project_redblack(fo_fluid *f, unsigned iters, float dt)
+{
+    float omega[128];
+    const float minRelaxation = 1.2f;
+    if (iters > 64) iters = 64;
+    for (unsigned iter = 0; iter < iters; iter++) {   /* schedule of fluid.go:169-170 */
+        float iterProgress = (float)iter / (float)iters;
+        float t = (f->Relaxation - minRelaxation) * iterProgress;
+        omega[2 * iter] = omega[2 * iter + 1] = f->Relaxation - t;
+    }
+    /* Red-black leaves the whole residual on the colour updated first; closing with
+     * a plain Gauss-Seidel red half sweep and a half-relaxed black one spreads it over
+     * both colours, which is what brings max|div| down to the lexicographic solver's. */
+    if (iters > 0) { omega[2 * iters - 2] = 1.0f; omega[2 * iters - 1] = 0.5f; }
+    return fo_project_redblack_sched(f, omega, iters, dt);
 }
 
 /* ---- edit command lists (test convenience; semantics = the point edits) ---- */

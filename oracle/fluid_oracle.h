@@ -105,6 +105,8 @@ int fo_run(fo_fluid *f, float dt, int64_t nsteps, const fo_edit_cmd *per_step, i
  * to check the CUDA fast mode bit for bit.  Returns max pre-update |div| of the
  * last iteration executed. */
 float fo_project_redblack(fo_fluid *f, unsigned iters, float dt);
+/* Same with an explicit omega per HALF sweep: omega[2k] red, omega[2k+1] black. */
+float fo_project_redblack_sched(fo_fluid *f, const float *omega, unsigned iters, float dt);
 
 #ifdef __cplusplus
 }
