@@ -18,6 +18,8 @@ U, V, NEWU, NEWV, P, S, M, NEWM = range(8)
 FIELD_NAMES = {"U": U, "V": V, "newU": NEWU, "newV": NEWV, "p": P, "S": S, "M": M, "newM": NEWM}
 # fb_solver
 SOLVER_EXACT, SOLVER_REDBLACK = 0, 1
+# fb_flags
+FLAG_LITERAL, FLAG_EXACT_SHADOW = 1, 2
 # fb_phase_id
 (PHASE_MAKE_INCOMPRESSIBLE, PHASE_ADVECT_VELOCITY, PHASE_ADVECT_SMOKE, PHASE_HANDLE_BORDERS, PHASE_CONFINEMENT,
  PHASE_TURBULENCE, PHASE_ADVECT_VELOCITY_BFECC, PHASE_ADVECT_SMOKE_BFECC, PHASE_VISCOSITY,
@@ -31,7 +33,8 @@ PROF_PHASES = ("edits", "clear_pressure", "viscosity", "project", "confinement",
 
 class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("density", C.c_float), ("h", C.c_float),
-                ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("ghost", C.c_int32)]
+                ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("ghost", C.c_int32),
+                ("flags", C.c_int32)]
 
 
 class Params(C.Structure):

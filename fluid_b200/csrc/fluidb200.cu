@@ -2,6 +2,8 @@
 // the C ABI declared in include/fluidb200.h.  The phase order and the buffer
 // semantics follow (*Fluid).Simulate, pkg/fluid/fluid.go:79-109 of the reference.
 #include "kernels.cuh"
+#include "advect_fused.cuh"
+#include "rb_fused.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -21,8 +23,16 @@ struct fb_handle {
     int device;
     cudaStream_t stream;
     size_t plane_floats;          // floats per device plane
-    float *f[FB_NFIELDS];
+    float *f[FB_NFIELDS];         // plane currently playing each role (roles swap, planes do not move)
     float *scr[SCR_N];
+    std::vector<float *> pool;    // free scratch planes of the fast path
+    unsigned char *mask;          // neighbour mask of S (advect_fused.cuh), rebuilt when S changes
+    bool mask_dirty;
+    bool literal;                 // FB_FLAG_LITERAL: reference-shaped kernels with physical copies
+    bool exact_shadow;            // FB_FLAG_EXACT_SHADOW: keep newU/newV/newM complete (white-box mode)
+    bool p_zero;                  // pressure plane known to be all zero
+    bool rb_attr_set;
+    int nsm;
     bool noise_ready;
     float *mirror[FB_NFIELDS];    // pinned host mirrors (lazy)
     unsigned *d_red;              // 64 reduction slots
@@ -88,6 +98,16 @@ static int scratch(fb_handle *h, int which, float **out)
     return FB_OK;
 }
 
+// scratch planes of the fast path: taken for an output, the plane they replace is given back
+static int take_plane(fb_handle *h, float **out)
+{
+    if (!h->pool.empty()) { *out = h->pool.back(); h->pool.pop_back(); return FB_OK; }
+    CK(cudaMalloc(out, h->plane_floats * sizeof(float)));
+    CK(cudaMemsetAsync(*out, 0, h->plane_floats * sizeof(float), h->stream));
+    return FB_OK;
+}
+static inline void give_plane(fb_handle *h, float *p) { h->pool.push_back(p); }
+
 // rows x columns launch geometry for full-plane kernels: x along j (unit stride)
 static inline void plane_launch(const Grid &g, int ib, int ie, dim3 &grid, dim3 &block, int cols = -1)
 {
@@ -144,6 +164,11 @@ extern "C" int fb_create(const fb_config *cfg, fb_handle **out)
         if (cfg->rank == 0) g.i_lo = 0;
         if (cfg->rank == nranks - 1) g.i_hi = g.NX;
     }
+    h->literal = (cfg->flags & FB_FLAG_LITERAL) != 0 || getenv("FLUIDB200_LITERAL") != nullptr;
+    h->exact_shadow = (cfg->flags & FB_FLAG_EXACT_SHADOW) != 0;
+    h->mask_dirty = true;
+    h->nsm = 148;
+    cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, h->device);
     int ghost = nranks > 1 ? (cfg->ghost > 0 ? cfg->ghost : 32) : 0;
     h->cfg.ghost = ghost;
     g.i_alloc0 = g.i_lo - ghost < 0 ? 0 : g.i_lo - ghost;
@@ -157,6 +182,8 @@ extern "C" int fb_create(const fb_config *cfg, fb_handle **out)
         CKC(cudaMalloc(&h->f[k], h->plane_floats * sizeof(float)));
         CKC(cudaMemsetAsync(h->f[k], 0, h->plane_floats * sizeof(float), h->stream));   // New(): all zero => all solid
     }
+    CKC(cudaMalloc(&h->mask, h->plane_floats));
+    CKC(cudaMemsetAsync(h->mask, 0, h->plane_floats, h->stream));
     CKC(cudaMalloc(&h->d_red, 64 * sizeof(unsigned)));
     CKC(cudaMemsetAsync(h->d_red, 0, 64 * sizeof(unsigned), h->stream));
     CKC(cudaMallocHost(&h->h_red, 64 * sizeof(unsigned)));
@@ -178,6 +205,8 @@ extern "C" int fb_destroy(fb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int k = 0; k < FB_NFIELDS; k++) { if (h->f[k]) cudaFree(h->f[k]); if (h->mirror[k]) cudaFreeHost(h->mirror[k]); }
     for (int k = 0; k < SCR_N; k++) if (h->scr[k]) cudaFree(h->scr[k]);
+    for (float *p : h->pool) cudaFree(p);
+    if (h->mask) cudaFree(h->mask);
     if (h->d_red) cudaFree(h->d_red);
     if (h->h_red) cudaFreeHost(h->h_red);
     if (h->d_bad) cudaFree(h->d_bad);
@@ -397,6 +426,8 @@ static int read_stats(fb_handle *h, unsigned iters)
     return FB_OK;
 }
 
+static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence);
+
 // makeIncompressible (fluid.go:144-155) + solveSingleGrid (fluid.go:157-186)
 static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsigned iters)
 {
@@ -421,6 +452,7 @@ static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsig
 
     if (p->solver == FB_SOLVER_EXACT) {
         if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "exact (lexicographic) solver is single-GPU only");
+        h->p_zero = false;
         // The early exit of fluid.go:175 depends on a full sweep's max|div|, which a
         // fused wavefront only knows afterwards: run optimistically from a backup
         // and, if some sweep k < iters-1 met the tolerance, replay exactly k+1 sweeps.
@@ -443,7 +475,10 @@ static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsig
         return FB_OK;
     }
 
+    if (!h->literal) return project_redblack_fused(h, p, dt, iters, false);
+
     // red-black, unfused reference path: one launch per half sweep
+    h->p_zero = false;
     int ib, ie; range(h, h->cfg.ghost, ib, ie);
     dim3 grid, block;
     plane_launch(h->g, ib, ie, grid, block, h->g.NY / 2 + 1);
@@ -460,6 +495,7 @@ static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsig
 static int clear_pressure(fb_handle *h)   // fluid.go:83
 {
     CK(cudaMemsetAsync(h->f[FB_P], 0, h->plane_floats * sizeof(float), h->stream));
+    h->p_zero = true;
     return FB_OK;
 }
 
@@ -597,12 +633,226 @@ static int advect_smoke_bfecc(fb_handle *h, const fb_params *p, float dt)   // f
     return FB_OK;
 }
 
+// ======================= fast path: fused kernels, pointer swaps =======================
+static int ensure_mask(fb_handle *h)
+{
+    if (!h->mask_dirty) return FB_OK;
+    const Grid &g = h->g;
+    const int ib = g.i_alloc0, ie = g.i_alloc0 + g.lines_alloc;
+    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    k_build_mask<<<grid, block, 0, h->stream>>>(g, h->f[FB_S], h->mask, ib, ie);
+    CKL("k_build_mask");
+    h->mask_dirty = false;
+    return FB_OK;
+}
+
+// newX := X as the reference's copy() leaves them, only when the caller asked for it
+static int sync_shadow(fb_handle *h, int live, int shadow)
+{
+    if (!h->exact_shadow) return FB_OK;
+    return copy_plane(h, h->f[shadow], h->f[live]);
+}
+
+// Geometry of the fused red-black pass for this grid.
+static void rb_geometry(const fb_handle *h, int ib, int ie, int &TJ, int &WL, int &nstrips, int &chunk, int &nchunks)
+{
+    const Grid &g = h->g;
+    nstrips = cdiv(g.NY, RB_TJ_MAX);
+    TJ = cdiv(cdiv(g.NY, nstrips), 4) * 4;
+    nstrips = cdiv(g.NY, TJ);
+    WL = TJ + 2 * RB_H + 4;
+    const int lines = ie - ib;
+    nchunks = h->nsm / nstrips;
+    if (nchunks < 1) nchunks = 1;
+    const int max_chunks = cdiv(lines, 48);           // keep the halo overhead (32 lines) bounded
+    if (nchunks > max_chunks) nchunks = max_chunks;
+    if (nchunks < 1) nchunks = 1;
+    chunk = cdiv(lines, nchunks);
+    nchunks = cdiv(lines, chunk);
+}
+
+// makeIncompressible with the red-black ordering, every iteration fused in one pass
+// over HBM (two passes when iters > 8).  Optionally applies addTurbulence to the lines
+// it writes.  Outputs go to fresh planes; roles are swapped afterwards.
+static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence)
+{
+    TRY(ensure_mask(h));
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    omega_schedule_redblack(p, iters, sp.omega);
+    { volatile float dh = h->cfg.density * h->cfg.h; sp.cp = dh / dt; }
+    int ib, ie; range(h, 0, ib, ie);
+    // with slabs the ghost lines are recomputed too, so that the next phase finds them current
+    if (h->cfg.nranks > 1) range(h, h->cfg.ghost - RB_H > 0 ? h->cfg.ghost - RB_H : 0, ib, ie);
+    int TJ, WL, nstrips, chunk, nchunks;
+    rb_geometry(h, ib, ie, TJ, WL, nstrips, chunk, nchunks);
+    const size_t smem = (size_t)RB_NL * WL * 13;
+    if (!h->rb_attr_set) {
+        CK(cudaFuncSetAttribute(k_rb_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        h->rb_attr_set = true;
+    }
+    float *nU = nullptr, *nV = nullptr;
+    if (fuse_turbulence) {
+        TRY(scratch(h, SCR_NOISEU, &nU)); TRY(scratch(h, SCR_NOISEV, &nV));
+        if (!h->noise_ready) {
+            const Grid &g = h->g;
+            dim3 grid, block; plane_launch(g, g.i_alloc0, g.i_alloc0 + g.lines_alloc, grid, block);
+            k_noise_init<<<grid, block, 0, h->stream>>>(g, nU, nV, g.i_alloc0, g.i_alloc0 + g.lines_alloc);
+            CKL("k_noise_init");
+            h->noise_ready = true;
+        }
+    }
+    unsigned done = 0;
+    while (done < iters) {
+        const unsigned k = iters - done < 8 ? iters - done : 8;
+        float *Uo, *Vo, *Po;
+        TRY(take_plane(h, &Uo)); TRY(take_plane(h, &Vo)); TRY(take_plane(h, &Po));
+        RBFused a;
+        memset(&a, 0, sizeof(a));
+        a.g = h->g;
+        a.U = h->f[FB_U]; a.V = h->f[FB_V];
+        a.Pin = h->p_zero ? nullptr : h->f[FB_P];
+        a.mask = h->mask;
+        a.Uo = Uo; a.Vo = Vo; a.Po = Po;
+        for (unsigned q = 0; q < 2 * k; q++) a.omega[q] = sp.omega[2 * done + q];
+        a.damping = p->pressure_damping; a.cp = sp.cp;
+        a.nstages = (int)(2 * k); a.stage0 = (int)(2 * done);
+        a.TJ = TJ; a.WL = WL; a.chunk = chunk; a.ib = ib; a.ie = ie;
+        a.stats = h->d_red;
+        const bool last = done + k == iters;
+        if (fuse_turbulence && last) {
+            volatile float ts = p->turbulence_strength * dt;
+            a.noiseU = nU; a.noiseV = nV; a.turb = ts;
+        }
+        k_rb_fused<<<dim3(nstrips, nchunks, 1), RB_THREADS, smem, h->stream>>>(a);
+        CKL("k_rb_fused");
+        give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]); give_plane(h, h->f[FB_P]);
+        h->f[FB_U] = Uo; h->f[FB_V] = Vo; h->f[FB_P] = Po;
+        h->p_zero = false;
+        done += k;
+    }
+    return FB_OK;
+}
+
+static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, bool do_confine, bool do_turb)
+{
+    if (!do_confine && !do_turb) return FB_OK;
+    TRY(ensure_mask(h));
+    float *nU = nullptr, *nV = nullptr;
+    const Grid &g = h->g;
+    if (do_turb) {
+        TRY(scratch(h, SCR_NOISEU, &nU)); TRY(scratch(h, SCR_NOISEV, &nV));
+        if (!h->noise_ready) {
+            dim3 grid, block; plane_launch(g, g.i_alloc0, g.i_alloc0 + g.lines_alloc, grid, block);
+            k_noise_init<<<grid, block, 0, h->stream>>>(g, nU, nV, g.i_alloc0, g.i_alloc0 + g.lines_alloc);
+            CKL("k_noise_init");
+            h->noise_ready = true;
+        }
+    }
+    float *dU, *dV;
+    TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
+    int ib, ie; range(h, h->cfg.nranks > 1 ? h->cfg.ghost - 2 : 0, ib, ie);
+    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    volatile float ts = do_turb ? p->turbulence_strength * dt : 0.0f;
+    k_confine_turbulence<<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
+                                                       do_confine ? p->confinement : 0.0f, ts, ib, ie);
+    CKL("k_confine_turbulence");
+    give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
+    h->f[FB_U] = dU; h->f[FB_V] = dV;
+    return FB_OK;
+}
+
+// advectVelocity: one kernel, roles swapped instead of copy(f.U, f.newU)
+static int advect_velocity_fast(fb_handle *h, float dt)
+{
+    TRY(ensure_mask(h));
+    float *dU, *dV;
+    TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_advect_velocity_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV],
+                                                         dU, dV, dt, h->cfg.h, ib, ie, h->d_bad);
+    CKL("k_advect_velocity_full");
+    give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
+    h->f[FB_U] = dU; h->f[FB_V] = dV;
+    TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
+    return FB_OK;
+}
+
+static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt)
+{
+    TRY(ensure_mask(h));
+    float *dM;
+    TRY(take_plane(h, &dM));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_advect_smoke_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
+                                                      h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    CKL("k_advect_smoke_full");
+    give_plane(h, h->f[FB_M]);
+    h->f[FB_M] = dM;
+    TRY(sync_shadow(h, FB_M, FB_NEWM));
+    return FB_OK;
+}
+
+// advectVelocityBFECC in three passes over complete planes (fluid.go:911-994)
+static int advect_velocity_bfecc_fast(fb_handle *h, float dt)
+{
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "BFECC needs halo exchanges between its passes; drive it per pass from the host layer");
+    TRY(ensure_mask(h));
+    float *fU, *fV, *cU, *cV;
+    TRY(take_plane(h, &fU)); TRY(take_plane(h, &fV)); TRY(take_plane(h, &cU)); TRY(take_plane(h, &cV));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    // pass 1: forward advection of the original field
+    k_advect_velocity_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV],
+                                                         fU, fV, dt, h->cfg.h, ib, ie, h->d_bad);
+    CKL("k_advect_velocity_full");
+    // pass 2: back-trace through the original velocities + compensation + clamp
+    k_bfecc_velocity_correct<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, fU, fV, cU, cV, dt, h->cfg.h,
+                                                           ib, ie, h->d_bad);
+    CKL("k_bfecc_velocity_correct");
+    // pass 3: the corrected field advects itself; skipped faces keep the stale scratch
+    // value, which after pass 1 is the forward result there == the old scratch value
+    float *oU = h->f[FB_U], *oV = h->f[FB_V];
+    k_advect_velocity_full<<<grid, block, 0, h->stream>>>(h->g, cU, cV, h->mask, h->f[FB_NEWU], h->f[FB_NEWV], oU, oV, dt,
+                                                         h->cfg.h, ib, ie, h->d_bad);
+    CKL("k_advect_velocity_full");
+    give_plane(h, fU); give_plane(h, fV); give_plane(h, cU); give_plane(h, cV);
+    TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
+    return FB_OK;
+}
+
+static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt)
+{
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "BFECC needs halo exchanges between its passes; drive it per pass from the host layer");
+    TRY(ensure_mask(h));
+    float *fM, *cM;
+    TRY(take_plane(h, &fM)); TRY(take_plane(h, &cM));
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    k_advect_smoke_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], fM, dt,
+                                                      h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    CKL("k_advect_smoke_full");
+    k_bfecc_smoke_correct<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, h->cfg.h,
+                                                        p->smoke_advection, ib, ie, h->d_bad);
+    CKL("k_bfecc_smoke_correct");
+    float *oM = h->f[FB_M];
+    k_advect_smoke_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
+                                                      h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    CKL("k_advect_smoke_full");
+    give_plane(h, fM); give_plane(h, cM);
+    TRY(sync_shadow(h, FB_M, FB_NEWM));
+    return FB_OK;
+}
+
 // ---- edits ----------------------------------------------------------------------------
 static EditFields edit_fields(fb_handle *h)
 {
     EditFields f;
     f.U = h->f[FB_U]; f.V = h->f[FB_V]; f.nU = h->f[FB_NEWU]; f.nV = h->f[FB_NEWV];
     f.P = h->f[FB_P]; f.S = h->f[FB_S]; f.M = h->f[FB_M]; f.nM = h->f[FB_NEWM];
+    f.latch_smoke = (!h->literal && !h->exact_shadow) ? 1 : 0;
     return f;
 }
 
@@ -653,6 +903,10 @@ static int run_edits(fb_handle *h, const fb_edit_cmd *cmds, size_t n, bool valid
         CK(cudaStreamSynchronize(h->stream));
     }
     const EditFields f = edit_fields(h);
+    for (size_t q = 0; q < n; q++) {
+        if (cmds[q].op == FB_EDIT_SET_SOLID || cmds[q].op == FB_EDIT_CIRCLE_OBSTACLE) h->mask_dirty = true;
+        if (cmds[q].op == FB_EDIT_RESET) h->p_zero = false;
+    }
     const long long SMALL = 1 << 14;
     size_t q = 0;
     while (q < n) {
@@ -732,18 +986,54 @@ extern "C" int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nstep
     const unsigned iters = p->iters > 0 ? (unsigned)p->iters : 8u;
     for (int s = 0; s < nsteps; s++) {
         { ProfScope ps(h, FB_PROF_EDITS); TRY(run_edits(h, per_step, n_per_step, false, s > 0)); }
-        { ProfScope ps(h, FB_PROF_CLEAR_PRESSURE); TRY(clear_pressure(h)); }               // fluid.go:83
-        if (p->viscosity_diffusion > 0.0f) { ProfScope ps(h, FB_PROF_VISCOSITY); TRY(apply_viscosity(h, p, dt)); }   // fluid.go:86-88
-        { ProfScope ps(h, FB_PROF_PROJECT); TRY(make_incompressible(h, p, dt, iters)); }   // fluid.go:90
-        if (p->confinement != 0.0f) { ProfScope ps(h, FB_PROF_CONFINEMENT); TRY(confinement(h, p, dt)); }   // fluid.go:92-94
-        if (p->turbulence_strength > 0.0f) { ProfScope ps(h, FB_PROF_TURBULENCE); TRY(turbulence(h, p, dt)); }   // fluid.go:97-99
-        { ProfScope ps(h, FB_PROF_BORDERS); TRY(handle_borders(h)); }                      // fluid.go:101
-        if (p->use_bfecc) {                                                                // fluid.go:102-108
-            { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_bfecc(h, dt)); }
-            { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc(h, p, dt)); }
+        if (h->literal) {
+            { ProfScope ps(h, FB_PROF_CLEAR_PRESSURE); TRY(clear_pressure(h)); }               // fluid.go:83
+            if (p->viscosity_diffusion > 0.0f) { ProfScope ps(h, FB_PROF_VISCOSITY); TRY(apply_viscosity(h, p, dt)); }   // fluid.go:86-88
+            { ProfScope ps(h, FB_PROF_PROJECT); TRY(make_incompressible(h, p, dt, iters)); }   // fluid.go:90
+            if (p->confinement != 0.0f) { ProfScope ps(h, FB_PROF_CONFINEMENT); TRY(confinement(h, p, dt)); }   // fluid.go:92-94
+            if (p->turbulence_strength > 0.0f) { ProfScope ps(h, FB_PROF_TURBULENCE); TRY(turbulence(h, p, dt)); }   // fluid.go:97-99
+            { ProfScope ps(h, FB_PROF_BORDERS); TRY(handle_borders(h)); }                      // fluid.go:101
+            if (p->use_bfecc) {                                                                // fluid.go:102-108
+                { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_bfecc(h, dt)); }
+                { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc(h, p, dt)); }
+            } else {
+                { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity(h, dt)); }
+                { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke(h, p, dt)); }
+            }
+            continue;
+        }
+        // fused path: same phase order, same arithmetic, fewer passes over HBM
+        const bool rb = p->solver == FB_SOLVER_REDBLACK;
+        const bool conf = p->confinement != 0.0f, turb = p->turbulence_strength > 0.0f;
+        if (rb) h->p_zero = true;                       // fill(p, 0) is folded into the fused solve
+        else { ProfScope ps(h, FB_PROF_CLEAR_PRESSURE); TRY(clear_pressure(h)); }
+        if (p->viscosity_diffusion > 0.0f) { ProfScope ps(h, FB_PROF_VISCOSITY); TRY(apply_viscosity(h, p, dt)); }
+        bool turb_done = false;
+        {
+            ProfScope ps(h, FB_PROF_PROJECT);
+            if (rb && iters > 0) {
+                TRY(copy_border(h, h->f[FB_NEWU], h->f[FB_U]));
+                TRY(copy_border(h, h->f[FB_NEWV], h->f[FB_V]));
+                CK(cudaMemsetAsync(h->d_red, 0, 32 * sizeof(unsigned), h->stream));
+                h->stats.sweeps_run = (int)iters; h->stats.rolled_back = 0;
+                turb_done = turb && !conf;              // turbulence rides on the solve's write-out
+                TRY(project_redblack_fused(h, p, dt, iters, turb_done));
+            } else {
+                if (rb) TRY(clear_pressure(h));
+                TRY(make_incompressible(h, p, dt, iters));
+            }
+        }
+        if (conf || (turb && !turb_done)) {
+            ProfScope ps(h, conf ? FB_PROF_CONFINEMENT : FB_PROF_TURBULENCE);
+            TRY(confine_turbulence_fast(h, p, dt, conf, turb));
+        }
+        { ProfScope ps(h, FB_PROF_BORDERS); TRY(handle_borders(h)); }
+        if (p->use_bfecc) {
+            { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_bfecc_fast(h, dt)); }
+            { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc_fast(h, p, dt)); }
         } else {
-            { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity(h, dt)); }
-            { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke(h, p, dt)); }
+            { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_fast(h, dt)); }
+            { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_fast(h, p, dt)); }
         }
     }
     return FB_OK;
@@ -756,13 +1046,13 @@ extern "C" int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float d
     TRY(check_params(h, p));
     switch (phase) {
     case FB_PHASE_MAKE_INCOMPRESSIBLE: return make_incompressible(h, p, dt, iters);
-    case FB_PHASE_ADVECT_VELOCITY: TRY(advect_velocity(h, dt)); return check_bad(h);
-    case FB_PHASE_ADVECT_SMOKE: TRY(advect_smoke(h, p, dt)); return check_bad(h);
+    case FB_PHASE_ADVECT_VELOCITY: TRY(h->literal ? advect_velocity(h, dt) : advect_velocity_fast(h, dt)); return check_bad(h);
+    case FB_PHASE_ADVECT_SMOKE: TRY(h->literal ? advect_smoke(h, p, dt) : advect_smoke_fast(h, p, dt)); return check_bad(h);
     case FB_PHASE_HANDLE_BORDERS: return handle_borders(h);
-    case FB_PHASE_CONFINEMENT: return confinement(h, p, dt);
-    case FB_PHASE_TURBULENCE: return turbulence(h, p, dt);
-    case FB_PHASE_ADVECT_VELOCITY_BFECC: return advect_velocity_bfecc(h, dt);
-    case FB_PHASE_ADVECT_SMOKE_BFECC: return advect_smoke_bfecc(h, p, dt);
+    case FB_PHASE_CONFINEMENT: return h->literal ? confinement(h, p, dt) : confine_turbulence_fast(h, p, dt, true, false);
+    case FB_PHASE_TURBULENCE: return h->literal ? turbulence(h, p, dt) : confine_turbulence_fast(h, p, dt, false, p->turbulence_strength > 0.0f);
+    case FB_PHASE_ADVECT_VELOCITY_BFECC: return h->literal ? advect_velocity_bfecc(h, dt) : advect_velocity_bfecc_fast(h, dt);
+    case FB_PHASE_ADVECT_SMOKE_BFECC: return h->literal ? advect_smoke_bfecc(h, p, dt) : advect_smoke_bfecc_fast(h, p, dt);
     case FB_PHASE_VISCOSITY: return apply_viscosity(h, p, dt);
     case FB_PHASE_CLEAR_PRESSURE: return clear_pressure(h);
     default: return fail(h, FB_ERR_INVALID, "unknown phase");
@@ -793,6 +1083,8 @@ extern "C" int fb_upload(fb_handle *h, int32_t field, const float *host)
     CK(cudaMemcpy2DAsync(d, (size_t)g.pitch * 4, src, (size_t)g.NY * 4, (size_t)g.NY * 4, (size_t)g.lines_alloc,
                          cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (field == FB_S) h->mask_dirty = true;
+    if (field == FB_P) h->p_zero = false;
     return FB_OK;
 }
 

@@ -672,7 +672,14 @@ __global__ void k_sample_velocity(Grid g, const float *__restrict__ U, const flo
 }
 
 // ---- edits (walls.go:5-93, fluid.go:761-771, 894-907) ------------------------------
-struct EditFields { float *U, *V, *nU, *nV, *P, *S, *M, *nM; };
+struct EditFields {
+    float *U, *V, *nU, *nV, *P, *S, *M, *nM;
+    // Fused path only: newM is kept current just where advection skips (solid cells), so
+    // a cell that turns solid latches its smoke there -- what the reference's newM holds
+    // (== M after the last advectSmoke, fluid.go:433) unless the caller edited that
+    // cell's smoke since the last Simulate (documented deviation).
+    int latch_smoke;
+};
 
 __device__ __forceinline__ void apply_edit_cell(const Grid &g, const EditFields &f, const fb_edit_cmd &c, int i, int j)
 {
@@ -689,6 +696,7 @@ __device__ __forceinline__ void apply_edit_cell(const Grid &g, const EditFields 
     }   // fallthrough: SetSolid(i, j, true)
     case FB_EDIT_SET_SOLID: {
         const bool solid = (c.op == FB_EDIT_CIRCLE_OBSTACLE) || (c.a != 0.0f);
+        if (solid && f.latch_smoke && f.S[a] != 0.0f) f.nM[a] = f.M[a];
         f.S[a] = solid ? 0.0f : 1.0f;
         if (solid) {
             f.U[a] = 0.0f; f.V[a] = 0.0f; f.nU[a] = 0.0f; f.nV[a] = 0.0f;

@@ -61,9 +61,12 @@ class Fluid:
 
     def __init__(self, density: float, width: int, height: int, h: float, *, device: int = 0,
                  solver: int = L.SOLVER_EXACT, rank: int = 0, nranks: int = 1, ghost: int = 0,
-                 compat: bool = False):
+                 compat: bool = False, literal: bool = False, exact_shadow: bool | None = None):
         self._h = C.c_void_p()
-        cfg = L.Config(width, height, density, h, device, rank, nranks, ghost)
+        if exact_shadow is None:
+            exact_shadow = compat     # white-box callers may rewrite S directly
+        flags = (L.FLAG_LITERAL if literal else 0) | (L.FLAG_EXACT_SHADOW if exact_shadow else 0)
+        cfg = L.Config(width, height, density, h, device, rank, nranks, ghost, flags)
         st = L.lib.fb_create(C.byref(cfg), C.byref(self._h))
         if st != L.FB_OK:
             self._h = C.c_void_p()

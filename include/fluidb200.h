@@ -61,7 +61,19 @@ typedef struct fb_config {
     int32_t device;          /* CUDA device ordinal */
     int32_t rank, nranks;    /* row-slab decomposition over i; 0,1 = single GPU */
     int32_t ghost;           /* ghost lines per side when nranks > 1 (0 = default) */
+    int32_t flags;           /* fb_flags, 0 = default */
 } fb_config;
+
+typedef enum fb_flags {
+    /* Reference-shaped kernels with the reference's physical array copies (the first,
+     * unfused implementation): kept for A/B parity checks of the fused path. */
+    FB_FLAG_LITERAL = 1,
+    /* Keep the scratch arrays newU/newV/newM complete after every advection, as the
+     * reference's copy(f.U, f.newU) does (fluid.go:331-332, 433).  Needed only when a
+     * caller rewrites S directly (white-box tests); the exported API never needs it
+     * because SetSolid zeroes both buffers (walls.go:19-48).  Costs 3 plane copies a step. */
+    FB_FLAG_EXACT_SHADOW = 2
+} fb_flags;
 
 /* The exported knobs of `type Fluid` (fluid.go:25-39), package var Relaxation
  * (fluid.go:7-9) and numIters (fluid.go:81).  Passed by value with every step

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from fluid_b200 import _lib, edits
-    assert ctypes.sizeof(_lib.Config) == 8 * 4
+    assert ctypes.sizeof(_lib.Config) == 9 * 4
     assert ctypes.sizeof(_lib.Params) == 11 * 4
     assert ctypes.sizeof(_lib.SolveStats) == 2 * 4 + 32 * 4
     assert edits.EDIT_DTYPE.itemsize == 7 * 4
@@ -46,7 +46,7 @@ def test_no_gpu_calls_fail_cleanly():
     assert abs(p.relaxation - 1.9) < 1e-6 and p.iters == 8 and abs(p.turbulence_strength - 0.02) < 1e-7
     assert _lib.lib.fb_version() >= 100
     h = ctypes.c_void_p()
-    cfg = _lib.Config(8, 8, 1.0, 1.0, 0, 0, 1, 0)
+    cfg = _lib.Config(8, 8, 1.0, 1.0, 0, 0, 1, 0, 0)
     st = _lib.lib.fb_create(ctypes.byref(cfg), ctypes.byref(h))
     if st == 0:
         assert _lib.lib.fb_destroy(h) == 0
