@@ -646,6 +646,26 @@ static int ensure_mask(fb_handle *h)
     return FB_OK;
 }
 
+static AdvCtx adv_ctx(const fb_handle *h)
+{
+    const Grid &g = h->g;
+    AdvCtx c;
+    c.NX = g.NX; c.NY = g.NY; c.pitch = g.pitch; c.i_alloc0 = g.i_alloc0; c.lines_alloc = g.lines_alloc;
+    volatile float hh = h->cfg.h;
+    volatile float h1 = 1.0f / hh, h2 = hh / 2.0f;
+    volatile float xmax = (float)g.NX * hh, ymax = (float)g.NY * hh;
+    c.h = hh; c.h1 = h1; c.h2 = h2; c.xmax = xmax; c.ymax = ymax;
+    c.nx1f = (float)(g.NX - 1); c.ny1f = (float)(g.NY - 1);
+    return c;
+}
+
+// launch helpers: CHECK (ghost-zone guard) only when the grid is split over ranks
+#define ADV_LAUNCH(kern, ...) do { \
+        dim3 _grid, _block; adv_launch(h->g.NY, ib, ie, _grid, _block); \
+        if (h->cfg.nranks > 1) kern<true><<<_grid, _block, 0, h->stream>>>(__VA_ARGS__); \
+        else kern<false><<<_grid, _block, 0, h->stream>>>(__VA_ARGS__); \
+        CKL(#kern); } while (0)
+
 // newX := X as the reference's copy() leaves them, only when the caller asked for it
 static int sync_shadow(fb_handle *h, int live, int shadow)
 {
@@ -752,10 +772,10 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
     float *dU, *dV;
     TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
     int ib, ie; range(h, h->cfg.nranks > 1 ? h->cfg.ghost - 2 : 0, ib, ie);
-    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    dim3 grid(cdiv(g.NY, CT_J), cdiv(ie - ib, CT_I), 1);
     volatile float ts = do_turb ? p->turbulence_strength * dt : 0.0f;
-    k_confine_turbulence<<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
-                                                       do_confine ? p->confinement : 0.0f, ts, ib, ie);
+    k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
+                                                                do_confine ? p->confinement : 0.0f, ts, ib, ie);
     CKL("k_confine_turbulence");
     give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
     h->f[FB_U] = dU; h->f[FB_V] = dV;
@@ -769,10 +789,8 @@ static int advect_velocity_fast(fb_handle *h, float dt)
     float *dU, *dV;
     TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
     int ib, ie; range(h, 0, ib, ie);
-    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
-    k_advect_velocity_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV],
-                                                         dU, dV, dt, h->cfg.h, ib, ie, h->d_bad);
-    CKL("k_advect_velocity_full");
+    const AdvCtx c = adv_ctx(h);
+    ADV_LAUNCH(k_advect_velocity_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], dU, dV, dt, ib, ie, h->d_bad);
     give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
     h->f[FB_U] = dU; h->f[FB_V] = dV;
     TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
@@ -785,10 +803,9 @@ static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt)
     float *dM;
     TRY(take_plane(h, &dM));
     int ib, ie; range(h, 0, ib, ie);
-    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
-    k_advect_smoke_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
-                                                      h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
-    CKL("k_advect_smoke_full");
+    const AdvCtx c = adv_ctx(h);
+    ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
+               p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
     give_plane(h, h->f[FB_M]);
     h->f[FB_M] = dM;
     TRY(sync_shadow(h, FB_M, FB_NEWM));
@@ -803,21 +820,15 @@ static int advect_velocity_bfecc_fast(fb_handle *h, float dt)
     float *fU, *fV, *cU, *cV;
     TRY(take_plane(h, &fU)); TRY(take_plane(h, &fV)); TRY(take_plane(h, &cU)); TRY(take_plane(h, &cV));
     int ib, ie; range(h, 0, ib, ie);
-    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
+    const AdvCtx c = adv_ctx(h);
     // pass 1: forward advection of the original field
-    k_advect_velocity_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV],
-                                                         fU, fV, dt, h->cfg.h, ib, ie, h->d_bad);
-    CKL("k_advect_velocity_full");
+    ADV_LAUNCH(k_advect_velocity_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], fU, fV, dt, ib, ie, h->d_bad);
     // pass 2: back-trace through the original velocities + compensation + clamp
-    k_bfecc_velocity_correct<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, fU, fV, cU, cV, dt, h->cfg.h,
-                                                           ib, ie, h->d_bad);
-    CKL("k_bfecc_velocity_correct");
+    ADV_LAUNCH(k_bfecc_velocity_correct, c, h->f[FB_U], h->f[FB_V], h->mask, fU, fV, cU, cV, dt, ib, ie, h->d_bad);
     // pass 3: the corrected field advects itself; skipped faces keep the stale scratch
     // value, which after pass 1 is the forward result there == the old scratch value
     float *oU = h->f[FB_U], *oV = h->f[FB_V];
-    k_advect_velocity_full<<<grid, block, 0, h->stream>>>(h->g, cU, cV, h->mask, h->f[FB_NEWU], h->f[FB_NEWV], oU, oV, dt,
-                                                         h->cfg.h, ib, ie, h->d_bad);
-    CKL("k_advect_velocity_full");
+    ADV_LAUNCH(k_advect_velocity_full, c, cU, cV, h->mask, h->f[FB_NEWU], h->f[FB_NEWV], oU, oV, dt, ib, ie, h->d_bad);
     give_plane(h, fU); give_plane(h, fV); give_plane(h, cU); give_plane(h, cV);
     TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
     return FB_OK;
@@ -830,17 +841,13 @@ static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt)
     float *fM, *cM;
     TRY(take_plane(h, &fM)); TRY(take_plane(h, &cM));
     int ib, ie; range(h, 0, ib, ie);
-    dim3 grid, block; plane_launch(h->g, ib, ie, grid, block);
-    k_advect_smoke_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], fM, dt,
-                                                      h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
-    CKL("k_advect_smoke_full");
-    k_bfecc_smoke_correct<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, h->cfg.h,
-                                                        p->smoke_advection, ib, ie, h->d_bad);
-    CKL("k_bfecc_smoke_correct");
+    const AdvCtx c = adv_ctx(h);
+    ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], fM, dt,
+               p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    ADV_LAUNCH(k_bfecc_smoke_correct, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, p->smoke_advection, ib, ie, h->d_bad);
     float *oM = h->f[FB_M];
-    k_advect_smoke_full<<<grid, block, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
-                                                      h->cfg.h, p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
-    CKL("k_advect_smoke_full");
+    ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
+               p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
     give_plane(h, fM); give_plane(h, cM);
     TRY(sync_shadow(h, FB_M, FB_NEWM));
     return FB_OK;
