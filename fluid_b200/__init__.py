@@ -7,5 +7,5 @@ include/fluidb200.h).  Importing this package fails if that library is absent:
 there is no CPU path.
 """
 from . import edits, presets  # noqa: F401
-from ._lib import FluidError, SOLVER_EXACT, SOLVER_REDBLACK  # noqa: F401
+from ._lib import FluidError, SOLVER_EXACT, SOLVER_REDBLACK, SOLVER_REDBLACK_PRESSURE  # noqa: F401
 from .fluid import Fluid, New, ScalarField, VectorField  # noqa: F401

@@ -17,7 +17,8 @@ STATUS = {0: "FB_OK", -1: "FB_ERR_INVALID", -2: "FB_ERR_CUDA", -3: "FB_ERR_NOMEM
 U, V, NEWU, NEWV, P, S, M, NEWM = range(8)
 FIELD_NAMES = {"U": U, "V": V, "newU": NEWU, "newV": NEWV, "p": P, "S": S, "M": M, "newM": NEWM}
 # fb_solver
-SOLVER_EXACT, SOLVER_REDBLACK = 0, 1
+SOLVER_EXACT, SOLVER_REDBLACK, SOLVER_REDBLACK_PRESSURE = 0, 1, 2
+OPT_SOLVE_STATS = 0
 # fb_flags
 FLAG_LITERAL, FLAG_EXACT_SHADOW = 1, 2
 # fb_phase_id
@@ -76,6 +77,7 @@ SYMBOLS = {
     "fb_timer_stop": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "fb_profile_enable": (C.c_int, [_H, C.c_int32]),
     "fb_profile_read": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "fb_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "fb_launch_count": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "fb_version": (C.c_int, []),
 }

@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "advect_fused.cuh"
 #include "rb_fused.cuh"
+#include "rbq_fused.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -31,7 +32,8 @@ struct fb_handle {
     bool literal;                 // FB_FLAG_LITERAL: reference-shaped kernels with physical copies
     bool exact_shadow;            // FB_FLAG_EXACT_SHADOW: keep newU/newV/newM complete (white-box mode)
     bool p_zero;                  // pressure plane known to be all zero
-    bool rb_attr_set;
+    bool rb_attr_set, rbq_attr_set;
+    bool want_stats;
     int nsm;
     bool noise_ready;
     float *mirror[FB_NFIELDS];    // pinned host mirrors (lazy)
@@ -167,6 +169,7 @@ extern "C" int fb_create(const fb_config *cfg, fb_handle **out)
     h->literal = (cfg->flags & FB_FLAG_LITERAL) != 0 || getenv("FLUIDB200_LITERAL") != nullptr;
     h->exact_shadow = (cfg->flags & FB_FLAG_EXACT_SHADOW) != 0;
     h->mask_dirty = true;
+    h->want_stats = true;
     h->nsm = 148;
     cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, h->device);
     int ghost = nranks > 1 ? (cfg->ghost > 0 ? cfg->ghost : 32) : 0;
@@ -268,6 +271,13 @@ extern "C" int fb_timer_stop(fb_handle *h, float *ms)
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return FB_OK;
+}
+
+extern "C" int fb_set_option(fb_handle *h, int32_t option, int32_t value)
+{
+    if (!h) return FB_ERR_INVALID;
+    if (option == FB_OPT_SOLVE_STATS) { h->want_stats = value != 0; return FB_OK; }
+    return fail(h, FB_ERR_INVALID, "unknown option");
 }
 
 extern "C" int fb_profile_enable(fb_handle *h, int32_t on)
@@ -475,7 +485,7 @@ static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsig
         return FB_OK;
     }
 
-    if (!h->literal) return project_redblack_fused(h, p, dt, iters, false);
+    if (!h->literal || p->solver == FB_SOLVER_REDBLACK_PRESSURE) return project_redblack_fused(h, p, dt, iters, false);
 
     // red-black, unfused reference path: one launch per half sweep
     h->p_zero = false;
@@ -722,7 +732,53 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             h->noise_ready = true;
         }
     }
+    const bool pressure_form = p->solver == FB_SOLVER_REDBLACK_PRESSURE;
+    if (pressure_form) {
+        TJ = cdiv(cdiv(h->g.NY, cdiv(h->g.NY, RQ_TJ_MAX)), 8) * 8;
+        nstrips = cdiv(h->g.NY, TJ);
+        WL = TJ + 2 * RQ_H + 8;
+        nchunks = h->nsm / nstrips; if (nchunks < 1) nchunks = 1;
+        const int max_chunks = cdiv(ie - ib, 48);
+        if (nchunks > max_chunks) nchunks = max_chunks;
+        if (nchunks < 1) nchunks = 1;
+        chunk = cdiv(ie - ib, nchunks); nchunks = cdiv(ie - ib, chunk);
+        if (!h->rbq_attr_set) {
+            CK(cudaFuncSetAttribute(k_rbq_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(k_rbq_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            h->rbq_attr_set = true;
+        }
+    }
     unsigned done = 0;
+    while (pressure_form && done < iters) {
+        const unsigned k = iters - done < 8 ? iters - done : 8;
+        float *Uo, *Vo, *Po;
+        TRY(take_plane(h, &Uo)); TRY(take_plane(h, &Vo)); TRY(take_plane(h, &Po));
+        RBQ a;
+        memset(&a, 0, sizeof(a));
+        a.g = h->g;
+        a.U = h->f[FB_U]; a.V = h->f[FB_V];
+        a.Pin = h->p_zero ? nullptr : h->f[FB_P];
+        a.mask = h->mask;
+        a.Uo = Uo; a.Vo = Vo; a.Po = Po;
+        for (unsigned q = 0; q < 2 * k; q++) { volatile float w = sp.omega[2 * done + q] * p->pressure_damping; a.wd[q] = w; }
+        a.cp = sp.cp;
+        a.nstages = (int)(2 * k); a.stage0 = (int)(2 * done);
+        a.TJ = TJ; a.WL = WL; a.chunk = chunk; a.ib = ib; a.ie = ie;
+        a.stats = h->d_red;
+        const bool last = done + k == iters;
+        if (fuse_turbulence && last) {
+            volatile float ts = p->turbulence_strength * dt;
+            a.noiseU = nU; a.noiseV = nV; a.turb = ts;
+        }
+        const size_t smem_q = (size_t)RQ_NL * WL * 13;
+        if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
+        else k_rbq_fused<false><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
+        CKL("k_rbq_fused");
+        give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]); give_plane(h, h->f[FB_P]);
+        h->f[FB_U] = Uo; h->f[FB_V] = Vo; h->f[FB_P] = Po;
+        h->p_zero = false;
+        done += k;
+    }
     while (done < iters) {
         const unsigned k = iters - done < 8 ? iters - done : 8;
         float *Uo, *Vo, *Po;
@@ -977,7 +1033,8 @@ extern "C" int fb_apply_force_radius(fb_handle *h, int32_t cx, int32_t cy, float
 static int check_params(fb_handle *h, const fb_params *p)
 {
     if (!p) return fail(h, FB_ERR_INVALID, "null params");
-    if (p->solver != FB_SOLVER_EXACT && p->solver != FB_SOLVER_REDBLACK) return fail(h, FB_ERR_INVALID, "unknown solver");
+    if (p->solver != FB_SOLVER_EXACT && p->solver != FB_SOLVER_REDBLACK && p->solver != FB_SOLVER_REDBLACK_PRESSURE)
+        return fail(h, FB_ERR_INVALID, "unknown solver");
     if (p->iters < 0 || p->iters > 32) return fail(h, FB_ERR_INVALID, "iters out of range");
     return FB_OK;
 }
@@ -1010,7 +1067,7 @@ extern "C" int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nstep
             continue;
         }
         // fused path: same phase order, same arithmetic, fewer passes over HBM
-        const bool rb = p->solver == FB_SOLVER_REDBLACK;
+        const bool rb = p->solver != FB_SOLVER_EXACT;
         const bool conf = p->confinement != 0.0f, turb = p->turbulence_strength > 0.0f;
         if (rb) h->p_zero = true;                       // fill(p, 0) is folded into the fused solve
         else { ProfScope ps(h, FB_PROF_CLEAR_PRESSURE); TRY(clear_pressure(h)); }

@@ -403,6 +403,9 @@ class Fluid:
         L.check(self._h, L.lib.fb_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def set_option(self, option: int, value: int):
+        L.check(self._h, L.lib.fb_set_option(self._h, option, value))
+
     def profile(self, on: bool = True):
         L.check(self._h, L.lib.fb_profile_enable(self._h, int(on)))
 

@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
             "fo_apply_edits": (C.c_int, [P, C.c_void_p, C.c_int64]),
             "fo_run": (C.c_int, [P, C.c_float, C.c_int64, C.c_void_p, C.c_int64]),
             "fo_project_redblack": (C.c_float, [P, C.c_uint, C.c_float]),
+            "fo_project_redblack_q": (C.c_float, [P, C.c_uint, C.c_float]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(l, name)
@@ -101,7 +102,7 @@ def lib() -> C.CDLL:
     return _lib
 
 
-SOLVER_EXACT, SOLVER_REDBLACK = 0, 1
+SOLVER_EXACT, SOLVER_REDBLACK, SOLVER_REDBLACK_PRESSURE = 0, 1, 2
 
 
 class ScalarField:
@@ -225,8 +226,12 @@ class OracleFluid:
         pass
 
     # ---- hot path
+    def _project_rb(self, iters, dt):
+        fn = self._l.fo_project_redblack_q if self.Solver == SOLVER_REDBLACK_PRESSURE else self._l.fo_project_redblack
+        return fn(self._f, iters, dt)
+
     def Simulate(self, dt):
-        if self.Solver == SOLVER_REDBLACK:
+        if self.Solver != SOLVER_EXACT:
             self._simulate_redblack(dt)
         else:
             self._l.fo_simulate(self._f, dt)
@@ -238,7 +243,7 @@ class OracleFluid:
         self.p[...] = 0
         if self.ViscosityDiffusion > 0:
             l.fo_apply_viscosity(f, dt)
-        l.fo_project_redblack(f, self.NumIters, dt)
+        self._project_rb(self.NumIters, dt)
         if self.Confinement != 0:
             l.fo_apply_vorticity_confinement(f, dt)
         if self.TurbulenceStrength > 0:
@@ -255,7 +260,7 @@ class OracleFluid:
         arr = None
         if per_step is not None and len(per_step):
             arr = np.ascontiguousarray(per_step)
-        if self.Solver == SOLVER_REDBLACK:
+        if self.Solver != SOLVER_EXACT:
             for _ in range(nsteps):
                 if arr is not None:
                     self.edit(arr)
@@ -267,8 +272,8 @@ class OracleFluid:
             raise IndexError("per-step edit out of range")
 
     def makeIncompressible(self, numIters, dt):
-        if self.Solver == SOLVER_REDBLACK:
-            self._l.fo_project_redblack(self._f, numIters, dt)
+        if self.Solver != SOLVER_EXACT:
+            self._project_rb(numIters, dt)
         else:
             self._l.fo_make_incompressible(self._f, numIters, dt)
 

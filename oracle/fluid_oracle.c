@@ -1050,6 +1050,95 @@ float fo_project_redblack(fo_fluid *f, unsigned iters, float dt)
     return fo_project_redblack_sched(f, omega, iters, dt);
 }
 
+/* ---- NOT in the reference: pressure-form red-black (see fluid_oracle.h) ----------
+ * Cell update (active colour):  nb = ((q[i-1,j] + q[i+1,j]) + q[i,j-1]) + q[i,j+1]
+ *                               q' = fma(wd*rs, nb - D0, fma(-wd, q, q))
+ * with wd = omega*PressureDamping, rs = 1/s (0 for cells the reference skips) and
+ * D0 the divergence of the field the pass started from.  Materialisation:
+ *   U[i,j] = (U0 - (S[i-1,j] ? q[i,j] : 0)) + (S[i,j] ? q[i-1,j] : 0),  V alike,
+ *   p[i,j] = fma(cp, q[i,j], p[i,j]). */
+static void redblack_q_pass(fo_fluid *f, const float *omega, unsigned iters, float cp)
+{
+    const int64_t n = f->NumY, NX = f->NumX, NY = f->NumY;
+    float *U = f->U, *V = f->V, *S = f->S, *P = f->p;
+    float *q = (float *)calloc((size_t)f->numCells, sizeof(float));
+    float *D0 = (float *)calloc((size_t)f->numCells, sizeof(float));
+    float *R = (float *)calloc((size_t)f->numCells, sizeof(float));
+    float *NS = (float *)calloc((size_t)f->numCells, sizeof(float));
+    static const float rs_of[5] = { 0.0f, 1.0f, 0.5f, 1.0f / 3.0f, 0.25f };
+    for (int64_t i = 1; i < NX - 1; i++)
+        for (int64_t j = 1; j < NY - 1; j++) {
+            if (S[i * n + j] == 0.0f) continue;
+            int ns = (S[(i - 1) * n + j] != 0.0f) + (S[(i + 1) * n + j] != 0.0f) + (S[i * n + j - 1] != 0.0f) +
+                     (S[i * n + j + 1] != 0.0f);
+            R[i * n + j] = rs_of[ns];
+            NS[i * n + j] = (float)ns;
+            D0[i * n + j] = ((U[(i + 1) * n + j] - U[i * n + j]) + V[i * n + j + 1]) - V[i * n + j];
+        }
+    float maxDiv = 0.0f;
+    for (unsigned it = 0; it < iters; it++) {
+        maxDiv = 0.0f;
+        for (int colour = 0; colour < 2; colour++) {
+            const float wd = omega[2 * it + colour] * f->PressureDamping;
+            for (int64_t i = 1; i < NX - 1; i++)
+                for (int64_t j = 1; j < NY - 1; j++) {
+                    if (((i + j) & 1) != colour) continue;
+                    const float rs = R[i * n + j];
+                    const float nb = ((q[(i - 1) * n + j] + q[(i + 1) * n + j]) + q[i * n + j - 1]) + q[i * n + j + 1];
+                    const float t = nb - D0[i * n + j];
+                    if (rs != 0.0f) {       /* pre-update divergence, for the statistics only */
+                        const float div = fmaf(NS[i * n + j], q[i * n + j], -t);
+                        if (fabsf(div) > maxDiv) maxDiv = fabsf(div);
+                    }
+                    const float cc = wd * rs;
+                    const float r0 = fmaf(-wd, q[i * n + j], q[i * n + j]);
+                    q[i * n + j] = fmaf(cc, t, r0);
+                }
+        }
+        f->last_maxdiv = maxDiv;
+    }
+    for (int64_t i = 0; i < NX; i++)
+        for (int64_t j = 0; j < NY; j++) {
+            const int c = S[i * n + j] != 0.0f;
+            const int xm = i > 0 && S[(i - 1) * n + j] != 0.0f;
+            const int ym = j > 0 && S[i * n + j - 1] != 0.0f;
+            const float qc = q[i * n + j];
+            const float qxm = i > 0 ? q[(i - 1) * n + j] : 0.0f;
+            const float qym = j > 0 ? q[i * n + j - 1] : 0.0f;
+            float a = xm ? qc : 0.0f, b = c ? qxm : 0.0f;
+            float t1 = U[i * n + j] - a;
+            U[i * n + j] = t1 + b;
+            a = ym ? qc : 0.0f; b = c ? qym : 0.0f;
+            t1 = V[i * n + j] - a;
+            V[i * n + j] = t1 + b;
+            P[i * n + j] = fmaf(cp, qc, P[i * n + j]);
+        }
+    free(q); free(D0); free(R); free(NS);
+}
+
+float fo_project_redblack_q(fo_fluid *f, unsigned iters, float dt)
+{
+    float omega[128];
+    const float minRelaxation = 1.2f;
+    if (iters > 64) iters = 64;
+    for (unsigned iter = 0; iter < iters; iter++) {
+        float iterProgress = (float)iter / (float)iters;
+        float t = (f->Relaxation - minRelaxation) * iterProgress;
+        omega[2 * iter] = omega[2 * iter + 1] = f->Relaxation - t;
+    }
+    if (iters > 0) { omega[2 * iters - 2] = 1.0f; omega[2 * iters - 1] = 0.5f; }
+    fo_copy_border(f, f->newU, f->U);
+    fo_copy_border(f, f->newV, f->V);
+    float cp = f->density * f->h / dt;
+    f->last_iters = (int)iters;
+    for (unsigned done = 0; done < iters; ) {       /* passes of at most 8 iterations, like the kernel */
+        unsigned k = iters - done < 8 ? iters - done : 8;
+        redblack_q_pass(f, omega + 2 * done, k, cp);
+        done += k;
+    }
+    return f->last_maxdiv;
+}
+
 /* ---- edit command lists (test convenience; semantics = the point edits) ---- */
 int fo_apply_edits(fo_fluid *f, const fo_edit_cmd *cmds, int64_t n)
 {

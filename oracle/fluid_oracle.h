@@ -105,6 +105,12 @@ int fo_run(fo_fluid *f, float dt, int64_t nsteps, const fo_edit_cmd *per_step, i
  * to check the CUDA fast mode bit for bit.  Returns max pre-update |div| of the
  * last iteration executed. */
 float fo_project_redblack(fo_fluid *f, unsigned iters, float dt);
+/* NOT in the reference: the same red-black iteration in PRESSURE FORM, restating the
+ * arithmetic of this repo's fastest CUDA solver (rbq_fused.cuh) operation for
+ * operation: per pass of <= 8 iterations, q accumulates the per-cell corrections
+ * against the frozen initial divergence D0, and U, V, p are materialised once at
+ * the end.  Algebraically identical to fo_project_redblack; rounding differs. */
+float fo_project_redblack_q(fo_fluid *f, unsigned iters, float dt);
 /* Same with an explicit omega per HALF sweep: omega[2k] red, omega[2k+1] black. */
 float fo_project_redblack_sched(fo_fluid *f, const float *omega, unsigned iters, float dt);
 

@@ -229,6 +229,60 @@ def test_redblack_solver_bit_exact_and_reaches_reference_residual(iters):
     g.close()
 
 
+@pytest.mark.parametrize("iters", [1, 3, 8, 11, 16])
+@pytest.mark.parametrize("size", [(200, 120), (520, 75), (61, 700)])
+def test_pressure_form_solver_bit_exact_vs_its_restatement(iters, size):
+    """FB_SOLVER_REDBLACK_PRESSURE (rbq_fused.cuh): bit-identical to the CPU restatement of
+    the same arithmetic (oracle fo_project_redblack_q), for pass splits 8+3 and 8+8 too, on
+    grids that exercise several strips / chunks; and equal to the face-form red-black solve
+    within float32 rounding (stated tolerance: 2e-5 max-abs on velocities of O(1..10))."""
+    import oracle
+    from fluid_b200 import presets
+    p = presets.karman(*size)
+    base = developed_state(p, steps=12)
+    cpu = oracle.New(p.density, p.width, p.height, p.h, solver=oracle.SOLVER_REDBLACK_PRESSURE)
+    copy_state(cpu, base)
+    g = gpu_clone(base, p, solver=2)
+    cpu.makeIncompressible(iters, p.dt)
+    g.makeIncompressible(iters, p.dt)
+    assert_state_equal(g, cpu, f"rbq{iters}")
+    st = g.solve_stats()
+    assert st["sweeps_run"] == iters
+    assert np.float32(st["max_div"][-1]) == np.float32(cpu.solve_stats()["last_max_div"])
+    face = oracle.New(p.density, p.width, p.height, p.h, solver=oracle.SOLVER_REDBLACK)
+    copy_state(face, base)
+    face.makeIncompressible(iters, p.dt)
+    for name in ("U", "V"):
+        r = diff_report(name, g.get(name), face.get(name))
+        assert r["max_abs"] <= 2e-5, r
+    g.close()
+
+
+@pytest.mark.parametrize("preset_name", ["jet", "cavity", "karman"])
+def test_pressure_form_multi_step_and_residual(preset_name):
+    """Whole steps with the throughput solver: bit-identical to its CPU restatement after 30
+    steps (fused turbulence in the solve's write-out included), and every step's residual
+    max|div| is not worse than the reference's lexicographic solve on the same input."""
+    import fluid_b200
+    import oracle
+    from fluid_b200 import presets
+    p = {"jet": presets.jet(210, 133), "cavity": presets.cavity(140, 140), "karman": presets.karman(260, 140)}[preset_name]
+    o, g = new_pair(p, solver=2)
+    o.step(p.dt, 30, p.per_step)
+    g.step(p.dt, 30, p.per_step)
+    assert_state_equal(g, o, f"rbq/{preset_name}")
+    # residual criterion on the developed state
+    o.edit(p.per_step)
+    lex = oracle.New(p.density, p.width, p.height, p.h)
+    copy_state(lex, o)
+    g2 = gpu_clone(o, p, solver=2)
+    lex.makeIncompressible(8, p.dt)
+    g2.makeIncompressible(8, p.dt)
+    assert g2.MaxDivergence() <= lex.MaxDivergence(), (g2.MaxDivergence(), lex.MaxDivergence())
+    g.close()
+    g2.close()
+
+
 def test_redblack_multi_step_bit_exact():
     import oracle
     from fluid_b200 import presets
