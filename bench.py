@@ -219,24 +219,26 @@ def main():
               "exact": fluid_b200.SOLVER_EXACT}[args.solver]
     preset = build_preset(pname, width, height, bfecc, conf)
 
-    # ---- N > 1: every rank runs the same per-GPU workload on its own device ("weak").
-    # The slab-decomposed path (halo exchange between ranks) is selected by the host layer
-    # when fluid_b200.parallel is available; see DESIGN.md "Multi-GPU".
-    parallel = None
+    # ---- N > 1: weak scaling -- the grid grows with N along i (row slabs, one per GPU), every
+    # rank steps its slab, halos go over NCCL (fluid_b200.parallel); N == 1 is the plain handle.
+    from fluid_b200 import parallel
     if world > 1:
-        try:
-            from fluid_b200 import parallel as parallel   # noqa: PLC0414
-        except Exception:
-            parallel = None
-
-    if parallel is not None and world > 1:
-        sim = parallel.SlabFluid(preset, solver=solver, device=local, rank=rank, nranks=world, weak=True)
+        if solver == fluid_b200.SOLVER_EXACT:
+            raise SystemExit("the lexicographic solver does not decompose into slabs; use --solver pressure")
+        preset = build_preset(pname, width * world, height, bfecc, conf)
+        reach = parallel.reach_for(preset.dt, preset.h, 8.0)          # jets run at 4; allow 2x
+        ghost = parallel.required_ghost(reach, bfecc, conf != 0.0)
+        sim = parallel.SlabFluid(preset.density, preset.width, preset.height, preset.h, solver=solver, device=local,
+                                 rank=rank, nranks=world, ghost=ghost, reach=reach)
+        sim.edit(preset.init)
+        sim.UseBFECC = bfecc
+        sim.Confinement = conf
         cells_total = sim.global_cells
-        parallelism = f"row-slabs x{world}, NCCL halo exchange"
+        parallelism = f"row slabs over i, {world} ranks, {ghost} ghost lines, 1 NCCL halo exchange per step"
     else:
         sim = make_fluid(fluid_b200, preset, solver, device=local)
-        cells_total = sim.NumX * sim.NumY * world
-        parallelism = "single GPU" if world == 1 else f"{world} independent replicas"
+        cells_total = sim.NumX * sim.NumY
+        parallelism = "single GPU"
 
     def run_steps(n):
         sim.step(preset.dt, n, preset.per_step)
@@ -298,7 +300,7 @@ def main():
     # ---- e2e: the frame loop through the public API with host buffers
     e2e = None
     secondary = {}
-    if (not args.no_secondary) and (parallel is None or world == 1):
+    if (not args.no_secondary) and world == 1:
         per = fluid_b200.edits.pack(preset.per_step)
         h2d = int(per.nbytes)
         mirror = sim._mirror(L.M)            # pinned host memory owned by the library
@@ -336,9 +338,40 @@ def main():
                      "note": "exact = lexicographic wavefront, bit-identical to the reference restatement"}
         sim.Solver = solver
 
+    if (not args.no_secondary) and world > 1:
+        # frame loop per rank: edit commands H2D, slab step (with its halo exchange), the rank's
+        # share of the Smoke() view D2H into pinned memory, min/max all-reduced
+        import ctypes as C
+        per = fluid_b200.edits.pack(preset.per_step)
+        mirror = sim.f._mirror(L.M)
+        mn, mx = C.c_float(), C.c_float()
+
+        def frame():
+            sim.step(preset.dt, 1, per)
+            L.check(sim.f._h, L.lib.fb_view(sim.f._h, L.VIEW_SMOKE, mirror.ctypes.data, C.byref(mn), C.byref(mx)))
+            t = torch.tensor([-mn.value, mx.value], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+        for _ in range(3):
+            frame()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": cells_total * args.steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(per.nbytes) * world,
+               "d2h_bytes_per_step": int(cells_total * 4 + 8 * world), "ms_per_step": e2e_s / args.steps * 1e3,
+               "what": "per step and rank: edit commands H2D, slab Simulate + halo exchange, slab of the Smoke() view D2H "
+                       "into pinned memory, min/max all-reduce"}
+
     # residual actually reached by the headline solver on the final state
     st = sim.solve_stats() if hasattr(sim, "solve_stats") else {}
     max_div_after = sim.MaxDivergence()
+    if world > 1:
+        sim.check_halo()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -350,7 +383,7 @@ def main():
             "metric": "cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "restates": cfg_desc, "grid_per_gpu": [width + 2, height + 2],
+            "config": {"workload": args.workload, "restates": cfg_desc, "grid_per_gpu": [width + 2, height + 2], "grid_total": [width * world + 2, height + 2],
                        "cells_total": cells_total, "preset": pname, "bfecc": bfecc, "confinement": conf,
                        "turbulence": 0.02, "dt": preset.dt, "parallelism": parallelism,
                        "solver": {"pressure": "red-black SOR in pressure form, 8 iterations fused in one pass, "

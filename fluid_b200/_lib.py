@@ -58,6 +58,7 @@ SYMBOLS = {
     "fb_default_params": (C.c_int, [C.POINTER(Params)]),
     "fb_dims": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fb_step": (C.c_int, [_H, C.POINTER(Params), C.c_float, C.c_int32, C.c_void_p, C.c_size_t]),
+    "fb_step_local": (C.c_int, [_H, C.POINTER(Params), C.c_float, C.c_int32, C.c_void_p, C.c_size_t]),
     "fb_phase": (C.c_int, [_H, C.c_int32, C.POINTER(Params), C.c_float, C.c_uint32]),
     "fb_get_solve_stats": (C.c_int, [_H, C.POINTER(SolveStats)]),
     "fb_edit": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
@@ -70,6 +71,7 @@ SYMBOLS = {
     "fb_sample_velocity": (C.c_int, [_H, C.c_size_t, C.c_void_p, C.c_void_p]),
     "fb_halo_region": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_size_t)]),
+    "fb_check_halo": (C.c_int, [_H]),
     "fb_ghost_lines": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "fb_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "fb_synchronize": (C.c_int, [_H]),

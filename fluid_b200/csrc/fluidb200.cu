@@ -44,6 +44,7 @@ struct fb_handle {
     int2 *d_order; int ntiles, nTa, nTb, order_T;
     int *d_tile_counter; int *d_done; int epoch;
     fb_edit_cmd *d_cmds; size_t d_cmds_cap;
+    std::vector<fb_edit_cmd> staged_cmds;   // host copy of what d_cmds holds (per-step lists repeat)
     cudaEvent_t ev0, ev1;
     bool prof;
     std::vector<cudaEvent_t> prof_pool;                 // recycled events
@@ -436,7 +437,7 @@ static int read_stats(fb_handle *h, unsigned iters)
     return FB_OK;
 }
 
-static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence);
+static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext = 0);
 
 // makeIncompressible (fluid.go:144-155) + solveSingleGrid (fluid.go:157-186)
 static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsigned iters)
@@ -558,9 +559,9 @@ static int turbulence(fb_handle *h, const fb_params *p, float dt)   // fluid.go:
     return FB_OK;
 }
 
-static int handle_borders(fb_handle *h)   // fluid.go:236-289
+static int handle_borders(fb_handle *h, int ext = 0)   // fluid.go:236-289
 {
-    int ib, ie; range(h, 0, ib, ie);
+    int ib, ie; range(h, ext, ib, ie);
     const int n = (ie - ib) + 2 * h->g.NY;
     k_handle_borders<<<cdiv(n, 256), 256, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], ib, ie);
     CKL("k_handle_borders");
@@ -704,16 +705,15 @@ static void rb_geometry(const fb_handle *h, int ib, int ie, int &TJ, int &WL, in
 // makeIncompressible with the red-black ordering, every iteration fused in one pass
 // over HBM (two passes when iters > 8).  Optionally applies addTurbulence to the lines
 // it writes.  Outputs go to fresh planes; roles are swapped afterwards.
-static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence)
+static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext)
 {
     TRY(ensure_mask(h));
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
     omega_schedule_redblack(p, iters, sp.omega);
     { volatile float dh = h->cfg.density * h->cfg.h; sp.cp = dh / dt; }
-    int ib, ie; range(h, 0, ib, ie);
-    // with slabs the ghost lines are recomputed too, so that the next phase finds them current
-    if (h->cfg.nranks > 1) range(h, h->cfg.ghost - RB_H > 0 ? h->cfg.ghost - RB_H : 0, ib, ie);
+    // with slabs `ext` ghost lines are recomputed too, so that the next phase finds them current
+    int ib, ie; range(h, ext, ib, ie);
     int TJ, WL, nstrips, chunk, nchunks;
     rb_geometry(h, ib, ie, TJ, WL, nstrips, chunk, nchunks);
     const size_t smem = (size_t)RB_NL * WL * 13;
@@ -810,7 +810,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
     return FB_OK;
 }
 
-static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, bool do_confine, bool do_turb)
+static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, bool do_confine, bool do_turb, int ext = 0)
 {
     if (!do_confine && !do_turb) return FB_OK;
     TRY(ensure_mask(h));
@@ -827,7 +827,7 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
     }
     float *dU, *dV;
     TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
-    int ib, ie; range(h, h->cfg.nranks > 1 ? h->cfg.ghost - 2 : 0, ib, ie);
+    int ib, ie; range(h, ext, ib, ie);
     dim3 grid(cdiv(g.NY, CT_J), cdiv(ie - ib, CT_I), 1);
     volatile float ts = do_turb ? p->turbulence_strength * dt : 0.0f;
     k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
@@ -839,12 +839,12 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
 }
 
 // advectVelocity: one kernel, roles swapped instead of copy(f.U, f.newU)
-static int advect_velocity_fast(fb_handle *h, float dt)
+static int advect_velocity_fast(fb_handle *h, float dt, int ext = 0)
 {
     TRY(ensure_mask(h));
     float *dU, *dV;
     TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
-    int ib, ie; range(h, 0, ib, ie);
+    int ib, ie; range(h, ext, ib, ie);
     const AdvCtx c = adv_ctx(h);
     ADV_LAUNCH(k_advect_velocity_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], dU, dV, dt, ib, ie, h->d_bad);
     give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
@@ -853,12 +853,12 @@ static int advect_velocity_fast(fb_handle *h, float dt)
     return FB_OK;
 }
 
-static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt)
+static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt, int ext = 0)
 {
     TRY(ensure_mask(h));
     float *dM;
     TRY(take_plane(h, &dM));
-    int ib, ie; range(h, 0, ib, ie);
+    int ib, ie; range(h, ext, ib, ie);
     const AdvCtx c = adv_ctx(h);
     ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
                p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
@@ -869,39 +869,41 @@ static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt)
 }
 
 // advectVelocityBFECC in three passes over complete planes (fluid.go:911-994)
-static int advect_velocity_bfecc_fast(fb_handle *h, float dt)
+static int advect_velocity_bfecc_fast(fb_handle *h, float dt, int ext_fwd = 0, int ext_corr = 0, int ext_final = 0)
 {
-    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "BFECC needs halo exchanges between its passes; drive it per pass from the host layer");
     TRY(ensure_mask(h));
     float *fU, *fV, *cU, *cV;
     TRY(take_plane(h, &fU)); TRY(take_plane(h, &fV)); TRY(take_plane(h, &cU)); TRY(take_plane(h, &cV));
-    int ib, ie; range(h, 0, ib, ie);
+    int ib, ie; range(h, ext_fwd, ib, ie);
     const AdvCtx c = adv_ctx(h);
     // pass 1: forward advection of the original field
     ADV_LAUNCH(k_advect_velocity_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], fU, fV, dt, ib, ie, h->d_bad);
     // pass 2: back-trace through the original velocities + compensation + clamp
+    range(h, ext_corr, ib, ie);
     ADV_LAUNCH(k_bfecc_velocity_correct, c, h->f[FB_U], h->f[FB_V], h->mask, fU, fV, cU, cV, dt, ib, ie, h->d_bad);
     // pass 3: the corrected field advects itself; skipped faces keep the stale scratch
     // value, which after pass 1 is the forward result there == the old scratch value
     float *oU = h->f[FB_U], *oV = h->f[FB_V];
+    range(h, ext_final, ib, ie);
     ADV_LAUNCH(k_advect_velocity_full, c, cU, cV, h->mask, h->f[FB_NEWU], h->f[FB_NEWV], oU, oV, dt, ib, ie, h->d_bad);
     give_plane(h, fU); give_plane(h, fV); give_plane(h, cU); give_plane(h, cV);
     TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
     return FB_OK;
 }
 
-static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt)
+static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt, int ext_fwd = 0, int ext_corr = 0)
 {
-    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "BFECC needs halo exchanges between its passes; drive it per pass from the host layer");
     TRY(ensure_mask(h));
     float *fM, *cM;
     TRY(take_plane(h, &fM)); TRY(take_plane(h, &cM));
-    int ib, ie; range(h, 0, ib, ie);
+    int ib, ie; range(h, ext_fwd, ib, ie);
     const AdvCtx c = adv_ctx(h);
     ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], fM, dt,
                p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    range(h, ext_corr, ib, ie);
     ADV_LAUNCH(k_bfecc_smoke_correct, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, p->smoke_advection, ib, ie, h->d_bad);
     float *oM = h->f[FB_M];
+    range(h, 0, ib, ie);
     ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
                p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
     give_plane(h, fM); give_plane(h, cM);
@@ -954,7 +956,10 @@ static int run_edits(fb_handle *h, const fb_edit_cmd *cmds, size_t n, bool valid
     if (n == 0) return FB_OK;
     if (!cmds) return FB_ERR_INVALID;
     if (validate) for (size_t q = 0; q < n; q++) TRY(validate_cmd(h, cmds[q]));
+    if (!staged && h->staged_cmds.size() == n && memcmp(h->staged_cmds.data(), cmds, n * sizeof(fb_edit_cmd)) == 0)
+        staged = true;                        // the same list is already on the device
     if (!staged) {
+        h->staged_cmds.assign(cmds, cmds + n);
         if (n > h->d_cmds_cap) {
             if (h->d_cmds) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_cmds)); h->d_cmds = nullptr; }
             size_t cap = n < 1024 ? 1024 : n * 2;
@@ -1101,6 +1106,74 @@ extern "C" int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nstep
         }
     }
     return FB_OK;
+}
+
+// One Simulate on this rank's slab of a grid split over ranks.  The caller has just
+// exchanged halos: the `ghost` lines of U, V and M on each side hold the neighbours'
+// current values.  No further communication happens inside the step: every phase is
+// recomputed redundantly on as many ghost lines as the phases after it will read
+// (`reach` = how many lines a semi-Lagrangian trace may travel, bilinear tap included).
+extern "C" int fb_step_local(fb_handle *h, const fb_params *p, float dt, int32_t reach,
+                             const fb_edit_cmd *per_step, size_t n_per_step)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    TRY(check_params(h, p));
+    if (p->solver == FB_SOLVER_EXACT && h->cfg.nranks > 1)
+        return fail(h, FB_ERR_UNSUPPORTED, "the lexicographic solver does not decompose into slabs; use a red-black solver");
+    if (h->literal) return fail(h, FB_ERR_UNSUPPORTED, "slab steps use the fused path");
+    if (p->viscosity_diffusion > 0.0f) return fail(h, FB_ERR_UNSUPPORTED, "viscosity is not available in slab steps");
+    if (n_per_step) for (size_t q = 0; q < n_per_step; q++) TRY(validate_cmd(h, per_step[q]));
+    const unsigned iters = p->iters > 0 ? (unsigned)p->iters : 8u;
+    if (iters > 8) return fail(h, FB_ERR_UNSUPPORTED, "slab steps fuse at most 8 iterations (one pass)");
+    const bool multi = h->cfg.nranks > 1;
+    const int G = h->cfg.ghost, w = reach < 1 ? 1 : reach;
+    const bool conf = p->confinement != 0.0f, turb = p->turbulence_strength > 0.0f;
+    // extents (ghost lines recomputed per phase), from the end of the step backwards
+    int e_smoke_fwd = 0, e_smoke_corr = 0, e_final = 1, e_corr = 0, e_fwd = 0, e_ct;
+    if (p->use_bfecc) {
+        e_smoke_corr = w; e_smoke_fwd = 2 * w;
+        e_final = 2 * w + 1; e_corr = e_final + w; e_fwd = e_corr + w;
+        e_ct = e_fwd + w;
+    } else {
+        e_ct = e_final + w;
+    }
+    const int e_proj = e_ct + (conf ? 2 : 0);
+    if (multi && (e_proj + RQ_H > G || 3 * w > G))
+        return fail(h, FB_ERR_HALO, "ghost zone too narrow for this reach; create the handle with more ghost lines");
+    if (!multi) { e_smoke_fwd = e_smoke_corr = e_final = e_corr = e_fwd = e_ct = 0; }
+    const int ep = multi ? e_proj : 0;
+
+    { ProfScope ps(h, FB_PROF_EDITS); TRY(run_edits(h, per_step, n_per_step, false, false)); }
+    h->p_zero = true;
+    bool turb_done = false;
+    {
+        ProfScope ps(h, FB_PROF_PROJECT);
+        CK(cudaMemsetAsync(h->d_red, 0, 32 * sizeof(unsigned), h->stream));
+        h->stats.sweeps_run = (int)iters; h->stats.rolled_back = 0;
+        turb_done = turb && !conf;
+        TRY(project_redblack_fused(h, p, dt, iters, turb_done, ep));
+    }
+    if (conf || (turb && !turb_done)) {
+        ProfScope ps(h, conf ? FB_PROF_CONFINEMENT : FB_PROF_TURBULENCE);
+        TRY(confine_turbulence_fast(h, p, dt, conf, turb, e_ct));
+    }
+    { ProfScope ps(h, FB_PROF_BORDERS); TRY(handle_borders(h, e_ct)); }
+    if (p->use_bfecc) {
+        { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_bfecc_fast(h, dt, e_fwd, e_corr, e_final)); }
+        { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc_fast(h, p, dt, e_smoke_fwd, e_smoke_corr)); }
+    } else {
+        { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_fast(h, dt, e_final)); }
+        { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_fast(h, p, dt, 0)); }
+    }
+    return FB_OK;   // ghost-zone violations are latched on the device: fb_check_halo
+}
+
+extern "C" int fb_check_halo(fb_handle *h)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    return check_bad(h);
 }
 
 extern "C" int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float dt, uint32_t iters)

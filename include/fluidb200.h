@@ -166,6 +166,14 @@ int fb_dims(const fb_handle *h, int64_t *num_x, int64_t *num_y,
 int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nsteps,
             const fb_edit_cmd *per_step, size_t n_per_step);
 int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float dt, uint32_t iters);
+/* One Simulate on this rank's slab (nranks > 1; also valid for nranks == 1).  The host
+ * layer exchanges `ghost` lines of U, V, M with both neighbours BEFORE each call
+ * (fb_halo_region); inside the step nothing is communicated: each phase is recomputed on
+ * as many ghost lines as later phases read.  `reach` bounds how many lines a trace may
+ * travel in one step, ceil(dt*max|u|/h) + 2; FB_ERR_HALO if the ghost zone cannot cover it
+ * or a trace leaves the lines this rank holds.  Red-black solvers only. */
+int fb_step_local(fb_handle *h, const fb_params *p, float dt, int32_t reach,
+                  const fb_edit_cmd *per_step, size_t n_per_step);
 int fb_get_solve_stats(fb_handle *h, fb_solve_stats *out);
 
 /* ---- edits (walls.go, fluid.go:761-796, 894-907) ------------------------ */
@@ -197,6 +205,9 @@ int fb_sample_velocity(fb_handle *h, size_t n, const float *xy, float *uv);
 int fb_halo_region(fb_handle *h, int32_t field, int32_t side, int32_t lines,
                    void **send_ptr, void **recv_ptr, size_t *bytes);
 int fb_ghost_lines(const fb_handle *h, int32_t *ghost);
+/* FB_ERR_HALO if any trace since the last check read outside the lines this rank holds
+ * (synchronises the stream; call it every few steps, not every step). */
+int fb_check_halo(fb_handle *h);
 
 /* ---- plumbing ----------------------------------------------------------- */
 int fb_stream(fb_handle *h, void **cuda_stream);   /* the stream all work is queued on */

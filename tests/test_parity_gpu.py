@@ -409,3 +409,62 @@ def test_parity_report_three_presets():
                     assert np.all(np.isfinite(g.get(name)))
             g.close()
     print("\nPARITY_REPORT " + repr(rows))
+
+
+@pytest.mark.parametrize("preset_name,nslabs", [("jet", 2), ("karman", 2), ("cavity", 3), ("karman_plain", 4)])
+def test_slab_decomposition_is_bit_identical(preset_name, nslabs):
+    """Row slabs with ghost lines, one halo exchange per step and redundant ghost
+    computation (fb_step_local) give exactly the single-domain result.  The slabs live in
+    one process here (exchange by device copies); the multi-process NCCL path runs the same
+    fb_step_local / fb_halo_region calls (tests/multi_gpu_check.py)."""
+    import fluid_b200
+    from fluid_b200 import presets
+    from fluid_b200.parallel import LocalSlabGroup, required_ghost
+    p = {"jet": presets.jet(330, 140), "karman": presets.karman(420, 150),
+         "cavity": presets.cavity(390, 130), "karman_plain": presets.karman(500, 90, bfecc=False, confinement=0.0)}[preset_name]
+    bfecc = bool(p.params.get("use_bfecc", False))
+    conf = float(p.params.get("confinement", 0.0)) != 0.0
+    reach = 6
+    ghost = required_ghost(reach, bfecc, conf)
+    single = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
+    group = LocalSlabGroup(p.density, p.width, p.height, p.h, nslabs, solver=2, ghost=ghost, reach=reach)
+    for f in (single, group):
+        f.edit(p.init)
+        f.UseBFECC = bfecc
+        f.Confinement = float(p.params.get("confinement", 0.0))
+        f.step(p.dt, 25, p.per_step)
+    for name in OBSERVABLE:
+        assert_bit_exact(f"slabs/{preset_name}:{name}", group.get(name), single.get(name))
+    group.close()
+    single.close()
+
+
+def test_step_local_single_rank_equals_step():
+    import fluid_b200
+    from fluid_b200 import presets
+    from fluid_b200.parallel import SlabFluid
+    p = presets.karman(200, 100)
+    a = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
+    b = SlabFluid(p.density, p.width, p.height, p.h, solver=2)
+    for f in (a, b):
+        f.edit(p.init)
+        f.UseBFECC = True
+        f.Confinement = 0.1
+        f.step(p.dt, 10, p.per_step)
+    for name in OBSERVABLE:
+        assert_bit_exact(name, b.get(name), a.get(name))
+    a.close()
+    b.close()
+
+
+def test_ghost_zone_too_narrow_is_an_error():
+    import fluid_b200
+    from fluid_b200 import presets
+    from fluid_b200.parallel import LocalSlabGroup
+    p = presets.karman(300, 80)
+    group = LocalSlabGroup(p.density, p.width, p.height, p.h, 2, solver=2, ghost=20, reach=6)
+    group.edit(p.init)
+    group.UseBFECC = True
+    with pytest.raises(fluid_b200.FluidError):
+        group.step(p.dt, 1, p.per_step)
+    group.close()
