@@ -734,9 +734,9 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
     }
     const bool pressure_form = p->solver == FB_SOLVER_REDBLACK_PRESSURE;
     if (pressure_form) {
-        TJ = cdiv(cdiv(h->g.NY, cdiv(h->g.NY, RQ_TJ_MAX)), 8) * 8;
+        TJ = cdiv(cdiv(h->g.NY, cdiv(h->g.NY, RQ_TJ_MAX)), 16) * 16;
         nstrips = cdiv(h->g.NY, TJ);
-        WL = TJ + 2 * RQ_H + 8;
+        WL = TJ + 2 * RQ_H + 16;
         nchunks = h->nsm / nstrips; if (nchunks < 1) nchunks = 1;
         const int max_chunks = cdiv(ie - ib, 48);
         if (nchunks > max_chunks) nchunks = max_chunks;
@@ -770,7 +770,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             volatile float ts = p->turbulence_strength * dt;
             a.noiseU = nU; a.noiseV = nV; a.turb = ts;
         }
-        const size_t smem_q = (size_t)RQ_NL * WL * 13;
+        const size_t smem_q = rq_smem_bytes(WL);   // planes + TMA staging ring + mbarriers + progress counters
         if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
         else k_rbq_fused<false><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
         CKL("k_rbq_fused");

@@ -16,10 +16,12 @@
 // Structure: a CTA owns `chunk` lines x TJ columns (+16-cell halo, recomputed).  Lines
 // (constant i, contiguous in j) stream through a ring of 35 slots in 220 KB of shared
 // memory.  24 warps form a software pipeline WITHOUT block-wide barriers:
-//   warps 16-19  loader   global U,V,mask -> -D0, 1/s, q=0 in slot(L)       (prefetch 1 line)
+//   thread 768   producer TMA bulk copies (cp.async.bulk + mbarrier) of the U, V, mask segments
+//                         of a line into a 4-deep staging ring, 4 lines ahead of the loader
+//   warps 16-19  loader   staging -> -D0, 1/s, q=0 in slot(L)
 //   warp  s<16   half sweep s (colour s&1): may process line r once its predecessor
 //                (loader for s=0, warp s-1 otherwise) has finished line r+1
-//   warps 20-23  writer   slot(r), slot(r-1) + U0,V0 -> U,V,p in global     (prefetch 1 line)
+//   warps 20-23  writer   slot(r), slot(r-1) + U0,V0 -> U,V,p in global     (register prefetch, 3 lines)
 // Each role publishes the last line it finished with st.release.cta and waits on its
 // predecessor with ld.acquire.cta; the loader reuses a slot once the writer is past it.
 // Even and odd columns live in separate arrays so one colour is contiguous: a lane
@@ -35,9 +37,16 @@
 
 #define RQ_NL 35          // line slots
 #define RQ_H 16
-#define RQ_THREADS 768
-#define RQ_TJ_MAX 456     // multiple of 8; WL = TJ + 40 <= 496 (WL/2 multiple of 4 for 128-bit LDS);
-                          // 35 * 496 * 13 B = 220.4 KB of shared memory
+#define RQ_THREADS 800
+#define RQ_TJ_MAX 416     // multiple of 16; WL = TJ + 48 <= 464 (16-byte granules for the TMA copies of the mask)
+#define RQ_STG 4          // staging ring depth (lines in flight through TMA)
+// shared memory: 35 slots * WL * 13 B (q, -D0, 1/s, mask) + RQ_STG * (WL*9 + 16) B staging + counters
+//                = 211.1 KB + 16.4 KB at WL = 464
+__host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
+__host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL)
+{
+    return (size_t)RQ_NL * WL * 13 + RQ_STG * rq_stage_bytes(WL) + 256;
+}
 
 struct RBQ {
     Grid g;
@@ -66,6 +75,38 @@ __device__ __forceinline__ void rq_st_release(int *p, int v)
 {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned rq_s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rq_mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rq_s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rq_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rq_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rq_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rq_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void rq_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(rq_s32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void rq_tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rq_s32(dst)), "l"(src), "r"(bytes), "r"(rq_s32(bar)) : "memory");
+}
+
 // all lanes of the warp return once *p >= need
 __device__ __forceinline__ void rq_wait_ge(const int *p, int need, int lane)
 {
@@ -139,12 +180,17 @@ template <bool STATS>
 __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int prog[20];     // [0] loader, [1+s] half sweep s, [17] writer: last line (relative) finished
     const int WL = P.WL, WQ = WL >> 1, ROW = WL;             // floats per slot in one plane
     float *sQ = reinterpret_cast<float *>(smem_raw);        // [slot][parity][q]
     float *sND = sQ + RQ_NL * WL;                            // -D0
     float *sR = sND + RQ_NL * WL;                            // 1/s (0: never updated)
     unsigned char *sM = reinterpret_cast<unsigned char *>(sR + RQ_NL * WL);
+    // staging ring: per slot WL floats of U, WL+4 floats of V, WL mask bytes (raw global data)
+    unsigned char *stg = sM + RQ_NL * WL;                    // 16-byte aligned: WL is a multiple of 8
+    const int STG = (int)rq_stage_bytes(WL);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(stg + RQ_STG * STG);   // RQ_STG mbarriers
+    // [0] loader, [1+s] half sweep s, [17] writer: last line (relative) each role finished
+    int *prog = reinterpret_cast<int *>(full + RQ_STG);
 
     const Grid g = P.g;
     const int NX = g.NX, NY = g.NY, PIT = g.pitch;
@@ -159,6 +205,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     const int nproc = e1 - e0;                                // lines each half sweep passes over
 
     if (tid < 20) prog[tid] = -1;
+    if (tid == 0) {
+        for (int k = 0; k < RQ_STG; k++) rq_mbar_init(full + k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     if (warp < 16) {
@@ -192,152 +242,190 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 + s) >> 1), __float_as_uint(mymax));
         }
     } else if (warp < 20) {
-        // ================= loader: lines e0 .. e1 =================
+        // ================= loader: staging -> slot, lines e0 .. e1 =================
         const int ld = tid - 512;
         const bool active = ld < (WL >> 2);
         const int j = jr0 + 4 * ld;
-        auto fetch = [&](int L, RQLine &x) {
-            x.u = x.u1 = x.v = make_float4(0.f, 0.f, 0.f, 0.f);
-            x.v4 = 0.0f; x.m = 0;
-            if (!active || L < 1 || L > NX - 2 || j < 0 || j >= PIT) return;       // only interior lines hold updatable cells
-            if (L < g.i_alloc0 || L + 1 >= g.i_alloc0 + g.lines_alloc) return;     // outside this rank's slab
-            const int o = (L - g.i_alloc0) * PIT + j;
-            x.m = __ldg(reinterpret_cast<const unsigned *>(P.mask + o));
-            x.u = ld4(P.U + o);
-            x.u1 = ld4(P.U + o + PIT);
-            x.v = ld4(P.V + o);
-            if (j + 4 < PIT) x.v4 = __ldg(P.V + o + 4);
-        };
-        auto commit = [&](int sl, const RQLine &x) {
-            if (!active) return;
-            float u0[4], u1[4], v[5], d[4], r[4];
-            unpack(x.u, u0); unpack(x.u1, u1); unpack(x.v, v); v[4] = x.v4;
-            unsigned mk = x.m;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned m = (mk >> (8 * k)) & 0xffu;
-                const int jj = j + k;
-                const int ns = __popc(m & 30u);
-                const bool upd = (m & MK_C) && ns > 0 && jj >= 1 && jj <= NY - 2;
-                const float dv = ((u1[k] - u0[k]) + v[k + 1]) - v[k];
-                d[k] = upd ? -dv : 0.0f;
-                r[k] = !upd ? 0.0f : (ns == 1 ? 1.0f : (ns == 2 ? 0.5f : (ns == 3 ? (1.0f / 3.0f) : 0.25f)));
-                if (!upd) mk &= ~(0xffu << (8 * k));
-            }
-            const int q = 2 * ld;
-            const int b0 = sl * ROW + q, b1 = b0 + WQ;
-            *reinterpret_cast<float2 *>(sND + b0) = make_float2(d[0], d[2]);
-            *reinterpret_cast<float2 *>(sND + b1) = make_float2(d[1], d[3]);
-            *reinterpret_cast<float2 *>(sR + b0) = make_float2(r[0], r[2]);
-            *reinterpret_cast<float2 *>(sR + b1) = make_float2(r[1], r[3]);
-            *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
-            *reinterpret_cast<float2 *>(sQ + b1) = make_float2(0.f, 0.f);
-            if (STATS) {   // updatable-cell bytes, only for the residual statistics
-                *reinterpret_cast<unsigned short *>(sM + b0) = (unsigned short)((mk & 0xffu) | ((mk >> 8) & 0xff00u));
-                *reinterpret_cast<unsigned short *>(sM + b1) = (unsigned short)(((mk >> 8) & 0xffu) | ((mk >> 16) & 0xff00u));
-            }
-        };
+        const bool col_in = active && j >= 0 && j < PIT;
         if (active) {   // the slot "below" line e0 (relative -1) must read as q = 0
             const int q = 2 * ld, b0 = (RQ_NL - 1) * ROW + q;
             *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
             *reinterpret_cast<float2 *>(sQ + b0 + WQ) = make_float2(0.f, 0.f);
         }
-        RQLine lnA, lnB;
-        fetch(e0, lnA);
         int sl = 0;
         const int *wprog = &prog[17];
         for (int rel = 0; rel <= nproc; rel++) {
+            const int L = e0 + rel;
+            // only interior lines inside this rank's slab hold updatable cells; line e1 is never swept
+            const bool line_live = rel < nproc && L >= 1 && L <= NX - 2 && L >= g.i_alloc0 &&
+                                   L + 1 < g.i_alloc0 + g.lines_alloc;
             // slot(rel) last held line rel-NL, which the writer reads while writing rel-NL and rel-NL+1
             if (rel >= RQ_NL - 1) rq_wait_ge(wprog, rel - RQ_NL + 1, lane);
-            if (rel & 1) { fetch(e0 + rel + 1, lnA); commit(sl, lnB); }
-            else         { fetch(e0 + rel + 1, lnB); commit(sl, lnA); }
+            float d[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned mk = 0;
+            if (rel < nproc) {
+                // lines rel and rel+1 must have landed (the producer stages every line 0 .. nproc)
+                rq_mbar_wait(full + (rel % RQ_STG), (rel / RQ_STG) & 1);
+                rq_mbar_wait(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1);
+            }
+            if (line_live && col_in) {
+                const unsigned char *s0 = stg + (rel % RQ_STG) * STG, *s1 = stg + ((rel + 1) % RQ_STG) * STG;
+                const float *stU = reinterpret_cast<const float *>(s0), *stV = stU + WL;
+                const float *stU1 = reinterpret_cast<const float *>(s1);
+                const unsigned char *stM = s0 + (size_t)(2 * WL + 4) * 4;
+                float u0[4], u1[4], v[5];
+                unpack(*reinterpret_cast<const float4 *>(stU + 4 * ld), u0);
+                unpack(*reinterpret_cast<const float4 *>(stU1 + 4 * ld), u1);
+                unpack(*reinterpret_cast<const float4 *>(stV + 4 * ld), v);
+                v[4] = (j + 4 < PIT) ? stV[4 * ld + 4] : 0.0f;
+                mk = *reinterpret_cast<const unsigned *>(stM + 4 * ld);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned m = (mk >> (8 * k)) & 0xffu;
+                    const int jj = j + k;
+                    const int ns = __popc(m & 30u);
+                    const bool upd = (m & MK_C) && ns > 0 && jj >= 1 && jj <= NY - 2;
+                    const float dv = ((u1[k] - u0[k]) + v[k + 1]) - v[k];
+                    d[k] = upd ? -dv : 0.0f;
+                    r[k] = !upd ? 0.0f : (ns == 1 ? 1.0f : (ns == 2 ? 0.5f : (ns == 3 ? (1.0f / 3.0f) : 0.25f)));
+                    if (!upd) mk &= ~(0xffu << (8 * k));
+                }
+            }
+            if (active) {
+                const int q = 2 * ld;
+                const int b0 = sl * ROW + q, b1 = b0 + WQ;
+                *reinterpret_cast<float2 *>(sND + b0) = make_float2(d[0], d[2]);
+                *reinterpret_cast<float2 *>(sND + b1) = make_float2(d[1], d[3]);
+                *reinterpret_cast<float2 *>(sR + b0) = make_float2(r[0], r[2]);
+                *reinterpret_cast<float2 *>(sR + b1) = make_float2(r[1], r[3]);
+                *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
+                *reinterpret_cast<float2 *>(sQ + b1) = make_float2(0.f, 0.f);
+                if (STATS) {   // updatable-cell bytes, only for the residual statistics
+                    *reinterpret_cast<unsigned short *>(sM + b0) = (unsigned short)((mk & 0xffu) | ((mk >> 8) & 0xff00u));
+                    *reinterpret_cast<unsigned short *>(sM + b1) = (unsigned short)(((mk >> 8) & 0xffu) | ((mk >> 16) & 0xff00u));
+                }
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 512) rq_st_release(&prog[0], rel);
             sl = sl + 1 == RQ_NL ? 0 : sl + 1;
         }
-    } else {
+    } else if (warp < 24) {
         // ================= writer: owned lines -> U, V, p =================
         const int st = tid - 640;
         const bool active = st < (P.TJ >> 2);
         const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
         const bool col_ok = active && w_j < NY;
-        float4 wU = make_float4(0, 0, 0, 0), wV = wU, wP = wU;
-        unsigned wM = 0;
-        auto wfetch = [&](int r) {
+        struct WIn { float4 u, v, p; unsigned m; };
+        WIn in[3];
+        auto wfetch = [&](int r, WIn &x) {
+            x.u = x.v = x.p = make_float4(0.f, 0.f, 0.f, 0.f);
+            x.m = 0;
             if (!col_ok || r < i0c || r >= i1c) return;
             const int o = (r - g.i_alloc0) * PIT + w_j;
-            wU = ld4(P.U + o);
-            wV = ld4(P.V + o);
-            wM = __ldg(reinterpret_cast<const unsigned *>(P.mask + o));
-            if (P.Pin) wP = ld4(P.Pin + o);
+            x.u = ld4(P.U + o);
+            x.v = ld4(P.V + o);
+            x.m = __ldg(reinterpret_cast<const unsigned *>(P.mask + o));
+            if (P.Pin) x.p = ld4(P.Pin + o);
         };
         const int *last = &prog[nst];                         // half sweep nst-1
-        wfetch(e0);
-        int sl = 0;
-        for (int rel = 0; rel < nproc; rel++) {
-            const int r = e0 + rel;
-            rq_wait_ge(last, rel, lane);
-            if (col_ok && r >= i0c && r < i1c) {
-                const int o = (r - g.i_alloc0) * PIT + w_j;
-                const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
-                const int q = w_lj >> 1;
-                float u[4], v[4], pin[4], qc[4], qx[4], ql;
-                unpack(wU, u); unpack(wV, v); unpack(wP, pin);
-                const unsigned m4 = wM;
-                {
-                    const float2 ev = *reinterpret_cast<const float2 *>(sQ + sl * ROW + q);
-                    const float2 od = *reinterpret_cast<const float2 *>(sQ + sl * ROW + WQ + q);
-                    qc[0] = ev.x; qc[1] = od.x; qc[2] = ev.y; qc[3] = od.y;
-                    const float2 evm = *reinterpret_cast<const float2 *>(sQ + slm * ROW + q);
-                    const float2 odm = *reinterpret_cast<const float2 *>(sQ + slm * ROW + WQ + q);
-                    qx[0] = evm.x; qx[1] = odm.x; qx[2] = evm.y; qx[3] = odm.y;
-                    ql = sQ[sl * ROW + WQ + q - 1];                  // column lj-1 (odd parity, index q-1)
-                }
-                wfetch(r + 1);                                       // inputs of the next line
-                const bool line_first = (r == 0);
-                float pu[4], pv[4], pp[4];
+        // only owned lines are written; progress is "last line finished", so publishing the
+        // first owned line also releases the slots of the halo lines before it
+        wfetch(i0c, in[0]); wfetch(i0c + 1, in[1]); wfetch(i0c + 2, in[2]);
+        int sl = (i0c - e0) % RQ_NL;
+        for (int r0 = i0c; r0 < i1c; r0 += 3) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const unsigned m = (m4 >> (8 * k)) & 0xffu;
-                    const float qym = (k == 0) ? ql : qc[k - 1 < 0 ? 0 : k - 1];
-                    const float a = (m & MK_XM) ? qc[k] : 0.0f;
-                    const float b = ((m & MK_C) && !line_first) ? qx[k] : 0.0f;
-                    const float t1 = u[k] - a;
-                    pu[k] = t1 + b;
-                    const float a2 = (m & MK_YM) ? qc[k] : 0.0f;
-                    const float b2 = ((m & MK_C) && (w_j + k) > 0) ? qym : 0.0f;
-                    const float t2 = v[k] - a2;
-                    pv[k] = t2 + b2;
-                    pp[k] = __fmaf_rn(P.cp, qc[k], P.Pin ? pin[k] : 0.0f);
-                }
-                if (P.turb > 0.0f && r >= 1 && r <= NX - 2) {        // fused addTurbulence (fluid.go:496-526)
+            for (int kk = 0; kk < 3; kk++) {
+                const int r = r0 + kk;
+                if (r >= i1c) break;
+                const int rel = r - e0;
+                rq_wait_ge(last, rel, lane);
+                if (col_ok) {
+                    const int o = (r - g.i_alloc0) * PIT + w_j;
+                    const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
+                    const int q = w_lj >> 1;
+                    float u[4], v[4], pin[4], qc[4], qx[4], ql;
+                    unpack(in[kk].u, u); unpack(in[kk].v, v); unpack(in[kk].p, pin);
+                    const unsigned m4 = in[kk].m;
+                    {
+                        const float2 ev = *reinterpret_cast<const float2 *>(sQ + sl * ROW + q);
+                        const float2 od = *reinterpret_cast<const float2 *>(sQ + sl * ROW + WQ + q);
+                        qc[0] = ev.x; qc[1] = od.x; qc[2] = ev.y; qc[3] = od.y;
+                        const float2 evm = *reinterpret_cast<const float2 *>(sQ + slm * ROW + q);
+                        const float2 odm = *reinterpret_cast<const float2 *>(sQ + slm * ROW + WQ + q);
+                        qx[0] = evm.x; qx[1] = odm.x; qx[2] = evm.y; qx[3] = odm.y;
+                        ql = sQ[sl * ROW + WQ + q - 1];                  // column lj-1 (odd parity, index q-1)
+                    }
+                    wfetch(r + 3, in[kk]);                               // keep 3 lines of inputs in flight
+                    const bool line_first = (r == 0);
+                    float pu[4], pv[4], pp[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const unsigned m = (m4 >> (8 * k)) & 0xffu;
-                        const int jj = w_j + k;
-                        if ((m & MK_C) && jj >= 1 && jj <= NY - 2) {
-                            const float uu = pu[k] * pu[k], vv = pv[k] * pv[k];
-                            const float localVel = sqrtf(uu + vv);
-                            if (localVel > 0.1f) {
-                                const float nu = __ldg(P.noiseU + o + k) * P.turb;
-                                const float nv = __ldg(P.noiseV + o + k) * P.turb;
-                                const float factor = fminf(localVel * 0.5f, 1.0f);
-                                const float du = nu * factor, dv = nv * factor;
-                                pu[k] = pu[k] + du;
-                                pv[k] = pv[k] + dv;
+                        const float qym = (k == 0) ? ql : qc[k - 1 < 0 ? 0 : k - 1];
+                        const float a = (m & MK_XM) ? qc[k] : 0.0f;
+                        const float b = ((m & MK_C) && !line_first) ? qx[k] : 0.0f;
+                        const float t1 = u[k] - a;
+                        pu[k] = t1 + b;
+                        const float a2 = (m & MK_YM) ? qc[k] : 0.0f;
+                        const float b2 = ((m & MK_C) && (w_j + k) > 0) ? qym : 0.0f;
+                        const float t2 = v[k] - a2;
+                        pv[k] = t2 + b2;
+                        pp[k] = __fmaf_rn(P.cp, qc[k], P.Pin ? pin[k] : 0.0f);
+                    }
+                    if (P.turb > 0.0f && r >= 1 && r <= NX - 2) {        // fused addTurbulence (fluid.go:496-526)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const unsigned m = (m4 >> (8 * k)) & 0xffu;
+                            const int jj = w_j + k;
+                            if ((m & MK_C) && jj >= 1 && jj <= NY - 2) {
+                                const float uu = pu[k] * pu[k], vv = pv[k] * pv[k];
+                                const float localVel = sqrtf(uu + vv);
+                                if (localVel > 0.1f) {
+                                    const float nu = __ldg(P.noiseU + o + k) * P.turb;
+                                    const float nv = __ldg(P.noiseV + o + k) * P.turb;
+                                    const float factor = fminf(localVel * 0.5f, 1.0f);
+                                    const float du = nu * factor, dv = nv * factor;
+                                    pu[k] = pu[k] + du;
+                                    pv[k] = pv[k] + dv;
+                                }
                             }
                         }
                     }
+                    store4(P.Uo + o, NY, w_j, pu);
+                    store4(P.Vo + o, NY, w_j, pv);
+                    store4(P.Po + o, NY, w_j, pp);
                 }
-                store4(P.Uo + o, NY, w_j, pu);
-                store4(P.Vo + o, NY, w_j, pv);
-                store4(P.Po + o, NY, w_j, pp);
-            } else {
-                wfetch(r + 1);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (tid == 640) rq_st_release(&prog[17], rel);
+                sl = sl + 1 == RQ_NL ? 0 : sl + 1;
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tid == 640) rq_st_release(&prog[17], rel);
-            sl = sl + 1 == RQ_NL ? 0 : sl + 1;
+        }
+    } else if (tid == 768) {
+        // ================= producer: TMA bulk copies into the staging ring =================
+        // line rel goes to staging slot rel % RQ_STG once the loader has consumed line rel - RQ_STG
+        // (the loader reads slot(rel) for lines rel-1 and rel, so it must be past line rel - RQ_STG).
+        const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
+        const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
+        for (int rel = 0; rel <= nproc; rel++) {
+            if (rel >= RQ_STG) {
+                while (rq_ld_acquire(&prog[0]) < rel - RQ_STG) __nanosleep(20);
+            }
+            const int L = e0 + rel;
+            unsigned long long *bar = full + (rel % RQ_STG);
+            const bool have = L >= 0 && L < NX && L >= g.i_alloc0 && L < g.i_alloc0 + g.lines_alloc && cjU > cj0;
+            if (!have) { rq_mbar_arrive(bar); continue; }
+            unsigned char *s0 = stg + (rel % RQ_STG) * STG;
+            float *stU = reinterpret_cast<float *>(s0), *stV = stU + WL;
+            unsigned char *stM = s0 + (size_t)(2 * WL + 4) * 4;
+            const int off = cj0 - jr0;                                        // staging column of global column cj0
+            const size_t o = (size_t)(L - g.i_alloc0) * PIT + cj0;
+            const unsigned bU = (unsigned)(cjU - cj0) * 4, bV = (unsigned)(cjV - cj0) * 4, bM = (unsigned)(cjU - cj0);
+            // order prior generic-proxy reads of this staging slot before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            rq_mbar_expect_tx(bar, bU + bV + bM);
+            rq_tma_load(stU + off, P.U + o, bU, bar);
+            rq_tma_load(stV + off, P.V + o, bV, bar);
+            rq_tma_load(stM + off, P.mask + o, bM, bar);
         }
     }
 }
