@@ -40,12 +40,12 @@
 #define RQ_THREADS 800
 #define RQ_TJ_MAX 416     // multiple of 16; WL = TJ + 48 <= 464 (16-byte granules for the TMA copies of the mask)
 #define RQ_STG 4          // staging ring depth (lines in flight through TMA)
-// shared memory: 35 slots * WL * 13 B (q, -D0, 1/s, mask) + RQ_STG * (WL*9 + 16) B staging + counters
-//                = 211.1 KB + 16.4 KB at WL = 464
+// shared memory: 35 slots * WL * 9 B (q, -D0, neighbour count) + RQ_STG * (WL*9 + 16) B staging
+//                + hand-off mbarriers = 146.2 KB + 16.4 KB + 4.6 KB at WL = 464
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL)
 {
-    return (size_t)RQ_NL * WL * 13 + RQ_STG * rq_stage_bytes(WL) + 256;
+    return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + 8 * RQ_STG + 8 * 18 * 32 + 64;
 }
 
 struct RBQ {
@@ -121,14 +121,22 @@ __device__ __forceinline__ void rq_publish(int *p, int v, int lane)
     if (lane == 0) rq_st_release(p, v);
 }
 
+// Carried across consecutive lines of one half sweep (registers): the `up` vector of
+// line r is the other-parity vector of line r+1, and the other-parity vector of line r
+// is the `down` vector of line r+1 (nobody writes them in between), so each line costs
+// 3 x LDS.128 + 2 x LDS.32 + 1 x STS.128 per 4 cells instead of 6 x LDS.128.
+struct RQCarry { float4 up[2], ot[2]; };
+
 // One line of one half sweep: the active cells have column parity A.
 template <int A, bool STATS>
-__device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__restrict__ sND, const float *__restrict__ sR,
-                                        const unsigned char *__restrict__ sM, int own_row, int up_row, int dn_row,
-                                        int WQ, int lane, float wd, bool row_owned, int TJ, float &mymax)
+__device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__restrict__ sND,
+                                        const unsigned char *__restrict__ sC, int own_row, int up_row, int dn_row,
+                                        int WQ, int lane, float wd, bool row_owned, int TJ, float &mymax,
+                                        RQCarry &cy, bool have)
 {
     const int ngrp = WQ >> 2;
-    const float2 wd2 = make_float2(wd, wd), nwd2 = make_float2(-wd, -wd);
+    const float2 nwd2 = make_float2(-wd, -wd);
+    const float c4 = wd * 0.25f;                          // wd * (1/s) for a cell with four fluid neighbours
     const int own = own_row + A * WQ, oth = own_row + (1 - A) * WQ;
     const int upo = up_row + A * WQ, dno = dn_row + A * WQ;
 #pragma unroll
@@ -139,36 +147,48 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__r
         float *qown = sQ + own + q0;
         const float4 qo = *reinterpret_cast<const float4 *>(qown);
         const float4 up = *reinterpret_cast<const float4 *>(sQ + upo + q0);
-        const float4 dn = *reinterpret_cast<const float4 *>(sQ + dno + q0);
-        const float4 ot = *reinterpret_cast<const float4 *>(sQ + oth + q0);
+        const float4 dn = have ? cy.ot[half] : *reinterpret_cast<const float4 *>(sQ + dno + q0);
+        const float4 ot = have ? cy.up[half] : *reinterpret_cast<const float4 *>(sQ + oth + q0);
+        cy.up[half] = up;
+        cy.ot[half] = ot;
         const float ox = sQ[oth + q0 + (A ? 4 : -1)];
         const float4 nd = *reinterpret_cast<const float4 *>(sND + own + q0);   // -D0
-        const float4 rs = *reinterpret_cast<const float4 *>(sR + own + q0);
+        const unsigned code = *reinterpret_cast<const unsigned *>(sC + own + q0);   // fluid-neighbour counts, 0 = skip
         // left / right neighbours of cell k: other-parity indices q0+k-1+A and q0+k+A
         float2 l01, l23, r01, r23;
         if (A) { l01 = make_float2(ot.x, ot.y); l23 = make_float2(ot.z, ot.w); r01 = make_float2(ot.y, ot.z); r23 = make_float2(ot.w, ox); }
         else   { l01 = make_float2(ox, ot.x);   l23 = make_float2(ot.y, ot.z); r01 = make_float2(ot.x, ot.y); r23 = make_float2(ot.z, ot.w); }
         // nb = ((q[i-1,j] + q[i+1,j]) + q[i,j-1]) + q[i,j+1];  t = nb - D0
-        float2 nb01 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.x, dn.y), make_float2(up.x, up.y)), l01), r01);
-        float2 nb23 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.z, dn.w), make_float2(up.z, up.w)), l23), r23);
+        const float2 nb01 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.x, dn.y), make_float2(up.x, up.y)), l01), r01);
+        const float2 nb23 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.z, dn.w), make_float2(up.z, up.w)), l23), r23);
         const float2 t01 = __fadd2_rn(nb01, make_float2(nd.x, nd.y));
         const float2 t23 = __fadd2_rn(nb23, make_float2(nd.z, nd.w));
         // q' = fma(wd*rs, t, fma(-wd, q, q))
         const float2 q01 = make_float2(qo.x, qo.y), q23 = make_float2(qo.z, qo.w);
-        const float2 c01 = __fmul2_rn(wd2, make_float2(rs.x, rs.y)), c23 = __fmul2_rn(wd2, make_float2(rs.z, rs.w));
+        float2 c01, c23;
+        if (code == 0x04040404u) {                       // the common case: four interior cells
+            c01 = make_float2(c4, c4); c23 = c01;
+        } else {
+            float c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned ns = (code >> (8 * k)) & 0xffu;
+                const float rs = ns == 0 ? 0.0f : (ns == 1 ? 1.0f : (ns == 2 ? 0.5f : (ns == 3 ? (1.0f / 3.0f) : 0.25f)));
+                c[k] = wd * rs;
+            }
+            c01 = make_float2(c[0], c[1]); c23 = make_float2(c[2], c[3]);
+        }
         const float2 n01 = __ffma2_rn(c01, t01, __ffma2_rn(nwd2, q01, q01));
         const float2 n23 = __ffma2_rn(c23, t23, __ffma2_rn(nwd2, q23, q23));
         *reinterpret_cast<float4 *>(qown) = make_float4(n01.x, n01.y, n23.x, n23.y);
         if (STATS) {
-            const unsigned mk = *reinterpret_cast<const unsigned *>(sM + own + q0);
             const float qv[4] = { qo.x, qo.y, qo.z, qo.w }, tv[4] = { t01.x, t01.y, t23.x, t23.y };
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const unsigned m = (mk >> (8 * k)) & 0xffu;
+                const unsigned ns = (code >> (8 * k)) & 0xffu;
                 const int lj = 2 * (q0 + k) + A;
-                if ((m & MK_C) && row_owned && lj >= RQ_H && lj < RQ_H + TJ) {
-                    const float ns = (float)__popc(m & 30u);
-                    const float ad = fabsf(__fmaf_rn(ns, qv[k], -tv[k]));
+                if (ns && row_owned && lj >= RQ_H && lj < RQ_H + TJ) {
+                    const float ad = fabsf(__fmaf_rn((float)ns, qv[k], -tv[k]));
                     if (ad > mymax) mymax = ad;
                 }
             }
@@ -176,21 +196,34 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__r
     }
 }
 
+// hand-off barriers: role 0 = loader, 1+s = half sweep s, 17 = writer; RQ_RING barriers per
+// role, one per line (line r uses barrier r % RQ_RING, phase parity (r / RQ_RING) & 1).
+// A role can lead its consumer by at most RQ_NL - 18 = 17 lines < RQ_RING, so a parity
+// wait always refers to the current or the immediately preceding phase.
+#define RQ_RING 32
+#define RQ_ROLES 18
+__device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line)
+{
+    rq_mbar_arrive(bars + role * RQ_RING + (line & (RQ_RING - 1)));
+}
+__device__ __forceinline__ void rq_wait_line(unsigned long long *bars, int role, int line)
+{
+    rq_mbar_wait(bars + role * RQ_RING + (line & (RQ_RING - 1)), (unsigned)(line / RQ_RING) & 1u);
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int WL = P.WL, WQ = WL >> 1, ROW = WL;             // floats per slot in one plane
+    const int WL = P.WL, WQ = WL >> 1, ROW = WL;             // elements per slot in one plane
     float *sQ = reinterpret_cast<float *>(smem_raw);        // [slot][parity][q]
     float *sND = sQ + RQ_NL * WL;                            // -D0
-    float *sR = sND + RQ_NL * WL;                            // 1/s (0: never updated)
-    unsigned char *sM = reinterpret_cast<unsigned char *>(sR + RQ_NL * WL);
+    unsigned char *sC = reinterpret_cast<unsigned char *>(sND + RQ_NL * WL);   // fluid-neighbour count, 0 = never updated
     // staging ring: per slot WL floats of U, WL+4 floats of V, WL mask bytes (raw global data)
-    unsigned char *stg = sM + RQ_NL * WL;                    // 16-byte aligned: WL is a multiple of 8
+    unsigned char *stg = sC + RQ_NL * WL;                    // 16-byte aligned: WL is a multiple of 16
     const int STG = (int)rq_stage_bytes(WL);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(stg + RQ_STG * STG);   // RQ_STG mbarriers
-    // [0] loader, [1+s] half sweep s, [17] writer: last line (relative) each role finished
-    int *prog = reinterpret_cast<int *>(full + RQ_STG);
+    unsigned long long *bars = full + RQ_STG;                // RQ_ROLES * RQ_RING hand-off mbarriers
 
     const Grid g = P.g;
     const int NX = g.NX, NY = g.NY, PIT = g.pitch;
@@ -204,11 +237,12 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     const int nst = P.nstages;
     const int nproc = e1 - e0;                                // lines each half sweep passes over
 
-    if (tid < 20) prog[tid] = -1;
-    if (tid == 0) {
-        for (int k = 0; k < RQ_STG; k++) rq_mbar_init(full + k, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
+        const int role = k / RQ_RING;
+        rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);
     }
+    if (tid < RQ_STG) rq_mbar_init(full + tid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     if (warp < 16) {
@@ -217,26 +251,29 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         if (s >= nst) return;
         const int colour = (P.stage0 + s) & 1;
         const float wd = P.wd[s];
-        const int *pred = &prog[s];                           // loader (s == 0) or half sweep s-1
-        int *mine = &prog[1 + s];
         float mymax = 0.0f;
         int sl = 0;
         int a = (colour + e0) & 1;
+        RQCarry cy;
+        bool have = false;
         for (int rel = 0; rel < nproc; rel++) {
-            rq_wait_ge(pred, rel + 1, lane);
+            rq_wait_line(bars, s, rel + 1);                   // predecessor (loader or half sweep s-1) is past line rel+1
             const int r = e0 + rel;
             if (r >= 1 && r <= NX - 2) {
                 const int slp = sl + 1 == RQ_NL ? 0 : sl + 1;
                 const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
                 const bool row_owned = (r >= i0c) && (r < i1c);
-                if (a) rq_line<1, STATS>(sQ, sND, sR, sM, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, P.TJ, mymax);
-                else   rq_line<0, STATS>(sQ, sND, sR, sM, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, P.TJ, mymax);
+                if (a) rq_line<1, STATS>(sQ, sND, sC, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, P.TJ, mymax, cy, have);
+                else   rq_line<0, STATS>(sQ, sND, sC, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, P.TJ, mymax, cy, have);
+                have = true;
+            } else {
+                have = false;
             }
-            rq_publish(mine, rel, lane);
+            rq_done(bars, 1 + s, rel);
             sl = sl + 1 == RQ_NL ? 0 : sl + 1;
             a ^= 1;
         }
-        rq_publish(mine, nproc, lane);     // line e1 is never swept: lets the next half sweep finish its last line
+        rq_done(bars, 1 + s, nproc);       // line e1 is never swept: lets the next half sweep finish its last line
         if (STATS) {
             mymax = warp_max(mymax);
             if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 + s) >> 1), __float_as_uint(mymax));
@@ -253,16 +290,23 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             *reinterpret_cast<float2 *>(sQ + b0 + WQ) = make_float2(0.f, 0.f);
         }
         int sl = 0;
-        const int *wprog = &prog[17];
+        const int last_owned = (i1c - 1) - e0;
         for (int rel = 0; rel <= nproc; rel++) {
             const int L = e0 + rel;
             // only interior lines inside this rank's slab hold updatable cells; line e1 is never swept
             const bool line_live = rel < nproc && L >= 1 && L <= NX - 2 && L >= g.i_alloc0 &&
                                    L + 1 < g.i_alloc0 + g.lines_alloc;
-            // slot(rel) last held line rel-NL, which the writer reads while writing rel-NL and rel-NL+1
-            if (rel >= RQ_NL - 1) rq_wait_ge(wprog, rel - RQ_NL + 1, lane);
-            float d[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
-            unsigned mk = 0;
+            // slot(rel) last held line y-1 with y = rel-NL+1; its last readers work on line y: the writer
+            // if y is an owned line, otherwise the last half sweep
+            {
+                const int y = rel - RQ_NL + 1;
+                if (y >= 0) {
+                    if (y >= RQ_H && y <= last_owned) rq_wait_line(bars, 17, y);
+                    else rq_wait_line(bars, nst, y);
+                }
+            }
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned code = 0;
             if (rel < nproc) {
                 // lines rel and rel+1 must have landed (the producer stages every line 0 .. nproc)
                 rq_mbar_wait(full + (rel % RQ_STG), (rel / RQ_STG) & 1);
@@ -278,17 +322,16 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 unpack(*reinterpret_cast<const float4 *>(stU1 + 4 * ld), u1);
                 unpack(*reinterpret_cast<const float4 *>(stV + 4 * ld), v);
                 v[4] = (j + 4 < PIT) ? stV[4 * ld + 4] : 0.0f;
-                mk = *reinterpret_cast<const unsigned *>(stM + 4 * ld);
+                const unsigned mk = *reinterpret_cast<const unsigned *>(stM + 4 * ld);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const unsigned m = (mk >> (8 * k)) & 0xffu;
                     const int jj = j + k;
-                    const int ns = __popc(m & 30u);
+                    const unsigned ns = __popc(m & 30u);
                     const bool upd = (m & MK_C) && ns > 0 && jj >= 1 && jj <= NY - 2;
                     const float dv = ((u1[k] - u0[k]) + v[k + 1]) - v[k];
                     d[k] = upd ? -dv : 0.0f;
-                    r[k] = !upd ? 0.0f : (ns == 1 ? 1.0f : (ns == 2 ? 0.5f : (ns == 3 ? (1.0f / 3.0f) : 0.25f)));
-                    if (!upd) mk &= ~(0xffu << (8 * k));
+                    if (upd) code |= ns << (8 * k);
                 }
             }
             if (active) {
@@ -296,17 +339,12 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 const int b0 = sl * ROW + q, b1 = b0 + WQ;
                 *reinterpret_cast<float2 *>(sND + b0) = make_float2(d[0], d[2]);
                 *reinterpret_cast<float2 *>(sND + b1) = make_float2(d[1], d[3]);
-                *reinterpret_cast<float2 *>(sR + b0) = make_float2(r[0], r[2]);
-                *reinterpret_cast<float2 *>(sR + b1) = make_float2(r[1], r[3]);
                 *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
                 *reinterpret_cast<float2 *>(sQ + b1) = make_float2(0.f, 0.f);
-                if (STATS) {   // updatable-cell bytes, only for the residual statistics
-                    *reinterpret_cast<unsigned short *>(sM + b0) = (unsigned short)((mk & 0xffu) | ((mk >> 8) & 0xff00u));
-                    *reinterpret_cast<unsigned short *>(sM + b1) = (unsigned short)(((mk >> 8) & 0xffu) | ((mk >> 16) & 0xff00u));
-                }
+                *reinterpret_cast<unsigned short *>(sC + b0) = (unsigned short)((code & 0xffu) | ((code >> 8) & 0xff00u));
+                *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)(((code >> 8) & 0xffu) | ((code >> 16) & 0xff00u));
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 512) rq_st_release(&prog[0], rel);
+            rq_done(bars, 0, rel);                            // all 128 loader threads arrive
             sl = sl + 1 == RQ_NL ? 0 : sl + 1;
         }
     } else if (warp < 24) {
@@ -327,9 +365,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             x.m = __ldg(reinterpret_cast<const unsigned *>(P.mask + o));
             if (P.Pin) x.p = ld4(P.Pin + o);
         };
-        const int *last = &prog[nst];                         // half sweep nst-1
-        // only owned lines are written; progress is "last line finished", so publishing the
-        // first owned line also releases the slots of the halo lines before it
+        // only owned lines are written; 3 lines of inputs are kept in flight
         wfetch(i0c, in[0]); wfetch(i0c + 1, in[1]); wfetch(i0c + 2, in[2]);
         int sl = (i0c - e0) % RQ_NL;
         for (int r0 = i0c; r0 < i1c; r0 += 3) {
@@ -338,7 +374,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 const int r = r0 + kk;
                 if (r >= i1c) break;
                 const int rel = r - e0;
-                rq_wait_ge(last, rel, lane);
+                rq_wait_line(bars, nst, rel);                 // last half sweep is past line r
                 if (col_ok) {
                     const int o = (r - g.i_alloc0) * PIT + w_j;
                     const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
@@ -355,7 +391,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                         qx[0] = evm.x; qx[1] = odm.x; qx[2] = evm.y; qx[3] = odm.y;
                         ql = sQ[sl * ROW + WQ + q - 1];                  // column lj-1 (odd parity, index q-1)
                     }
-                    wfetch(r + 3, in[kk]);                               // keep 3 lines of inputs in flight
+                    wfetch(r + 3, in[kk]);
                     const bool line_first = (r == 0);
                     float pu[4], pv[4], pp[4];
 #pragma unroll
@@ -395,21 +431,18 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                     store4(P.Vo + o, NY, w_j, pv);
                     store4(P.Po + o, NY, w_j, pp);
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                if (tid == 640) rq_st_release(&prog[17], rel);
+                rq_done(bars, 17, rel);                       // all 128 writer threads arrive
                 sl = sl + 1 == RQ_NL ? 0 : sl + 1;
             }
         }
     } else if (tid == 768) {
         // ================= producer: TMA bulk copies into the staging ring =================
-        // line rel goes to staging slot rel % RQ_STG once the loader has consumed line rel - RQ_STG
-        // (the loader reads slot(rel) for lines rel-1 and rel, so it must be past line rel - RQ_STG).
+        // line rel goes to staging slot rel % RQ_STG once the loader is past line rel - RQ_STG
+        // (the loader reads staging slot(rel) for lines rel-1 and rel).
         const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
         const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
         for (int rel = 0; rel <= nproc; rel++) {
-            if (rel >= RQ_STG) {
-                while (rq_ld_acquire(&prog[0]) < rel - RQ_STG) __nanosleep(20);
-            }
+            if (rel >= RQ_STG) rq_wait_line(bars, 0, rel - RQ_STG);
             const int L = e0 + rel;
             unsigned long long *bar = full + (rel % RQ_STG);
             const bool have = L >= 0 && L < NX && L >= g.i_alloc0 && L < g.i_alloc0 + g.lines_alloc && cjU > cj0;
