@@ -248,12 +248,29 @@ extern "C" int fb_ghost_lines(const fb_handle *h, int32_t *ghost)
 
 extern "C" int fb_stream(fb_handle *h, void **s) { if (!h || !s) return FB_ERR_INVALID; *s = (void *)h->stream; return FB_OK; }
 
+// The fused solver's warp pipeline gives up (instead of hanging the GPU) when a hand-off
+// never arrives; the flag it leaves behind becomes an error here.
+static int check_pipeline(fb_handle *h)
+{
+    int dbg[6] = {0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(dbg, h->d_red + 48, sizeof(dbg), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (dbg[0]) {
+        char msg[200];
+        snprintf(msg, sizeof(msg), "fused solver pipeline timed out: waited-for role %d line %d, thread %d, block (%d,%d), parity %d",
+                 dbg[1] >> 20, dbg[1] & 0xfffff, dbg[2], dbg[3], dbg[4], dbg[5]);
+        CK(cudaMemsetAsync(h->d_red + 48, 0, sizeof(dbg), h->stream));
+        return fail(h, FB_ERR_CUDA, msg);
+    }
+    return FB_OK;
+}
+
 extern "C" int fb_synchronize(fb_handle *h)
 {
     if (!h) return FB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    return FB_OK;
+    return check_pipeline(h);
 }
 
 extern "C" int fb_timer_start(fb_handle *h)
@@ -765,6 +782,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         a.nstages = (int)(2 * k); a.stage0 = (int)(2 * done);
         a.TJ = TJ; a.WL = WL; a.chunk = chunk; a.ib = ib; a.ie = ie;
         a.stats = h->d_red;
+        a.debug = reinterpret_cast<int *>(h->d_red + 48);
         const bool last = done + k == iters;
         if (fuse_turbulence && last) {
             volatile float ts = p->turbulence_strength * dt;
@@ -1201,6 +1219,7 @@ extern "C" int fb_get_solve_stats(fb_handle *h, fb_solve_stats *out)
     if (!h || !out) return FB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (h->stats.rolled_back == 0) TRY(read_stats(h, (unsigned)h->stats.sweeps_run));
+    TRY(check_pipeline(h));
     *out = h->stats;
     return FB_OK;
 }

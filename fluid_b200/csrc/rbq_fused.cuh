@@ -41,11 +41,11 @@
 #define RQ_TJ_MAX 416     // multiple of 16; WL = TJ + 48 <= 464 (16-byte granules for the TMA copies of the mask)
 #define RQ_STG 4          // staging ring depth (lines in flight through TMA)
 // shared memory: 35 slots * WL * 9 B (q, -D0, neighbour count) + RQ_STG * (WL*9 + 16) B staging
-//                + hand-off mbarriers = 146.2 KB + 16.4 KB + 4.6 KB at WL = 464
+//                + hand-off mbarriers = 146.2 KB + 16.4 KB + 9.2 KB at WL = 464
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL)
 {
-    return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + 8 * RQ_STG + 8 * 18 * 32 + 64;
+    return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + 8 * RQ_STG + 8 * 18 * 64 + 64;
 }
 
 struct RBQ {
@@ -59,6 +59,7 @@ struct RBQ {
     int nstages, stage0;
     int TJ, WL, chunk, ib, ie;
     unsigned *stats;             // per-iteration max |div| (only when STATS)
+    int *debug;                  // [0] != 0: a pipeline wait timed out, [1..5] say which
     const float *noiseU, *noiseV;
     float turb;
 };
@@ -88,17 +89,36 @@ __device__ __forceinline__ void rq_mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rq_s32(bar)) : "memory");
 }
-__device__ __forceinline__ void rq_mbar_wait(unsigned long long *bar, unsigned parity)
+__device__ __forceinline__ bool rq_mbar_try(unsigned long long *bar, unsigned parity)
 {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(rq_s32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(rq_s32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline that stops making progress must never hang the GPU.  After
+// ~2^22 failed polls (hundreds of milliseconds) the first waiter records who waited for
+// what in P.debug and every waiter falls through; the host turns the flag into an error.
+__device__ int *rq_debug;   // set per launch (RBQ::debug)
+__device__ __forceinline__ void rq_mbar_wait(unsigned long long *bar, unsigned parity, int tag = 0)
+{
+    for (unsigned spin = 0; !rq_mbar_try(bar, parity); spin++) {
+        if ((spin & 1023u) == 1023u) {
+            int *d = rq_debug;
+            if (d && *reinterpret_cast<volatile int *>(d) != 0) return;     // someone already gave up: drain
+            if (spin > (1u << 21)) {
+                if (d && atomicCAS(d, 0, 1) == 0) {
+                    d[1] = tag; d[2] = (int)threadIdx.x; d[3] = (int)blockIdx.x; d[4] = (int)blockIdx.y; d[5] = (int)parity;
+                    __threadfence();
+                }
+                return;
+            }
+        }
+    }
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void rq_tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
@@ -198,9 +218,10 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__r
 
 // hand-off barriers: role 0 = loader, 1+s = half sweep s, 17 = writer; RQ_RING barriers per
 // role, one per line (line r uses barrier r % RQ_RING, phase parity (r / RQ_RING) & 1).
-// A role can lead its consumer by at most RQ_NL - 18 = 17 lines < RQ_RING, so a parity
-// wait always refers to the current or the immediately preceding phase.
-#define RQ_RING 32
+// Every role arrives for EVERY line 0 .. nproc in order, and no role can be more than
+// RQ_NL lines ahead of another (the loader waits for the slot), so with RQ_RING > RQ_NL a
+// parity wait always refers to the current or the immediately preceding phase.
+#define RQ_RING 64
 #define RQ_ROLES 18
 __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line)
 {
@@ -208,7 +229,7 @@ __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int 
 }
 __device__ __forceinline__ void rq_wait_line(unsigned long long *bars, int role, int line)
 {
-    rq_mbar_wait(bars + role * RQ_RING + (line & (RQ_RING - 1)), (unsigned)(line / RQ_RING) & 1u);
+    rq_mbar_wait(bars + role * RQ_RING + (line & (RQ_RING - 1)), (unsigned)(line / RQ_RING) & 1u, (role << 20) | line);
 }
 
 template <bool STATS>
@@ -237,6 +258,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     const int nst = P.nstages;
     const int nproc = e1 - e0;                                // lines each half sweep passes over
 
+    if (tid == 0) rq_debug = P.debug;
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
         rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);
@@ -309,8 +331,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             unsigned code = 0;
             if (rel < nproc) {
                 // lines rel and rel+1 must have landed (the producer stages every line 0 .. nproc)
-                rq_mbar_wait(full + (rel % RQ_STG), (rel / RQ_STG) & 1);
-                rq_mbar_wait(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1);
+                rq_mbar_wait(full + (rel % RQ_STG), (rel / RQ_STG) & 1, (30 << 20) | rel);
+                rq_mbar_wait(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1, (31 << 20) | rel);
             }
             if (line_live && col_in) {
                 const unsigned char *s0 = stg + (rel % RQ_STG) * STG, *s1 = stg + ((rel + 1) % RQ_STG) * STG;
@@ -365,7 +387,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             x.m = __ldg(reinterpret_cast<const unsigned *>(P.mask + o));
             if (P.Pin) x.p = ld4(P.Pin + o);
         };
-        // only owned lines are written; 3 lines of inputs are kept in flight
+        // only owned lines are written, but the hand-off phases count every line: arrive for the halo lines first
+        for (int rel = 0; rel < i0c - e0; rel++) rq_done(bars, 17, rel);
+        // 3 lines of inputs are kept in flight
         wfetch(i0c, in[0]); wfetch(i0c + 1, in[1]); wfetch(i0c + 2, in[2]);
         int sl = (i0c - e0) % RQ_NL;
         for (int r0 = i0c; r0 < i1c; r0 += 3) {
