@@ -783,6 +783,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         a.TJ = TJ; a.WL = WL; a.chunk = chunk; a.ib = ib; a.ie = ie;
         a.stats = h->d_red;
         a.debug = reinterpret_cast<int *>(h->d_red + 48);
+        { const char *x = getenv("FLUIDB200_RBQ_X"); a.xflags = x ? atoi(x) : 0; }
         const bool last = done + k == iters;
         if (fuse_turbulence && last) {
             volatile float ts = p->turbulence_strength * dt;

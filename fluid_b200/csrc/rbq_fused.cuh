@@ -60,6 +60,7 @@ struct RBQ {
     int TJ, WL, chunk, ib, ie;
     unsigned *stats;             // per-iteration max |div| (only when STATS)
     int *debug;                  // [0] != 0: a pipeline wait timed out, [1..5] say which
+    int xflags;                  // experiments (FLUIDB200_RBQ_X): 1 skip sweeps, 2 skip writer I/O, 4 skip TMA
     const float *noiseU, *noiseV;
     float turb;
 };
@@ -223,6 +224,8 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__r
 // parity wait always refers to the current or the immediately preceding phase.
 #define RQ_RING 64
 #define RQ_ROLES 18
+// Every lane arrives and every lane polls: measured faster than one arrive / one poller per
+// warp (lane-0 polling adds a divergent branch + __syncwarp to every hand-off: 0.35 -> 0.59 ms).
 __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line)
 {
     rq_mbar_arrive(bars + role * RQ_RING + (line & (RQ_RING - 1)));
@@ -230,6 +233,10 @@ __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int 
 __device__ __forceinline__ void rq_wait_line(unsigned long long *bars, int role, int line)
 {
     rq_mbar_wait(bars + role * RQ_RING + (line & (RQ_RING - 1)), (unsigned)(line / RQ_RING) & 1u, (role << 20) | line);
+}
+__device__ __forceinline__ void rq_wait_warp(unsigned long long *bar, unsigned parity, int tag)
+{
+    rq_mbar_wait(bar, parity, tag);
 }
 
 template <bool STATS>
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     if (tid == 0) rq_debug = P.debug;
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);
+        rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);  // arrivals per phase = threads of the role
     }
     if (tid < RQ_STG) rq_mbar_init(full + tid, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         for (int rel = 0; rel < nproc; rel++) {
             rq_wait_line(bars, s, rel + 1);                   // predecessor (loader or half sweep s-1) is past line rel+1
             const int r = e0 + rel;
-            if (r >= 1 && r <= NX - 2) {
+            if (r >= 1 && r <= NX - 2 && !(P.xflags & 1)) {
                 const int slp = sl + 1 == RQ_NL ? 0 : sl + 1;
                 const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
                 const bool row_owned = (r >= i0c) && (r < i1c);
@@ -331,8 +338,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             unsigned code = 0;
             if (rel < nproc) {
                 // lines rel and rel+1 must have landed (the producer stages every line 0 .. nproc)
-                rq_mbar_wait(full + (rel % RQ_STG), (rel / RQ_STG) & 1, (30 << 20) | rel);
-                rq_mbar_wait(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1, (31 << 20) | rel);
+                rq_wait_warp(full + (rel % RQ_STG), (rel / RQ_STG) & 1, (30 << 20) | rel);
+                rq_wait_warp(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1, (31 << 20) | rel);
             }
             if (line_live && col_in) {
                 const unsigned char *s0 = stg + (rel % RQ_STG) * STG, *s1 = stg + ((rel + 1) % RQ_STG) * STG;
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 *reinterpret_cast<unsigned short *>(sC + b0) = (unsigned short)((code & 0xffu) | ((code >> 8) & 0xff00u));
                 *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)(((code >> 8) & 0xffu) | ((code >> 16) & 0xff00u));
             }
-            rq_done(bars, 0, rel);                            // all 128 loader threads arrive
+            rq_done(bars, 0, rel);                            // one arrive per loader warp
             sl = sl + 1 == RQ_NL ? 0 : sl + 1;
         }
     } else if (warp < 24) {
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 if (r >= i1c) break;
                 const int rel = r - e0;
                 rq_wait_line(bars, nst, rel);                 // last half sweep is past line r
-                if (col_ok) {
+                if (col_ok && !(P.xflags & 2)) {
                     const int o = (r - g.i_alloc0) * PIT + w_j;
                     const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
                     const int q = w_lj >> 1;
@@ -455,34 +462,61 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                     store4(P.Vo + o, NY, w_j, pv);
                     store4(P.Po + o, NY, w_j, pp);
                 }
-                rq_done(bars, 17, rel);                       // all 128 writer threads arrive
+                rq_done(bars, 17, rel);                       // one arrive per writer warp
                 sl = sl + 1 == RQ_NL ? 0 : sl + 1;
             }
         }
     } else if (tid == 768) {
         // ================= producer: TMA bulk copies into the staging ring =================
         // line rel goes to staging slot rel % RQ_STG once the loader is past line rel - RQ_STG
-        // (the loader reads staging slot(rel) for lines rel-1 and rel).
+        // (the loader reads staging slot(rel) for lines rel-1 and rel).  One thread: everything
+        // that does not change from line to line is hoisted, the loop body is ~30 instructions.
         const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
         const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
-        for (int rel = 0; rel <= nproc; rel++) {
-            if (rel >= RQ_STG) rq_wait_line(bars, 0, rel - RQ_STG);
-            const int L = e0 + rel;
-            unsigned long long *bar = full + (rel % RQ_STG);
-            const bool have = L >= 0 && L < NX && L >= g.i_alloc0 && L < g.i_alloc0 + g.lines_alloc && cjU > cj0;
-            if (!have) { rq_mbar_arrive(bar); continue; }
-            unsigned char *s0 = stg + (rel % RQ_STG) * STG;
-            float *stU = reinterpret_cast<float *>(s0), *stV = stU + WL;
-            unsigned char *stM = s0 + (size_t)(2 * WL + 4) * 4;
-            const int off = cj0 - jr0;                                        // staging column of global column cj0
-            const size_t o = (size_t)(L - g.i_alloc0) * PIT + cj0;
-            const unsigned bU = (unsigned)(cjU - cj0) * 4, bV = (unsigned)(cjV - cj0) * 4, bM = (unsigned)(cjU - cj0);
-            // order prior generic-proxy reads of this staging slot before the async-proxy writes
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            rq_mbar_expect_tx(bar, bU + bV + bM);
-            rq_tma_load(stU + off, P.U + o, bU, bar);
-            rq_tma_load(stV + off, P.V + o, bV, bar);
-            rq_tma_load(stM + off, P.mask + o, bM, bar);
+        const int off = cj0 - jr0;                                            // staging column of global column cj0
+        const unsigned bU = (unsigned)(cjU - cj0) * 4, bV = (unsigned)(cjV - cj0) * 4, bM = (unsigned)(cjU - cj0);
+        const unsigned bytes = bU + bV + bM;
+        // lines that exist in this rank's planes: relative [relA, relB)
+        const int lineA = max(0, g.i_alloc0), lineB = min(NX, g.i_alloc0 + g.lines_alloc);
+        const int relA = lineA - e0, relB = (cjU > cj0 && !(P.xflags & 4)) ? lineB - e0 : -1;
+        unsigned dU[RQ_STG], dV[RQ_STG], dM[RQ_STG], fb[RQ_STG];
+#pragma unroll
+        for (int k = 0; k < RQ_STG; k++) {
+            unsigned char *s0 = stg + k * STG;
+            dU[k] = rq_s32(reinterpret_cast<float *>(s0) + off);
+            dV[k] = rq_s32(reinterpret_cast<float *>(s0) + WL + off);
+            dM[k] = rq_s32(s0 + (size_t)(2 * WL + 4) * 4 + off);
+            fb[k] = rq_s32(full + k);
+        }
+        const long long o0 = (long long)(e0 - g.i_alloc0) * PIT + cj0;       // offset of relative line 0 (may be negative)
+        const float *gU = P.U + o0, *gV = P.V + o0;
+        const unsigned char *gM = P.mask + o0;
+        const unsigned lbase = rq_s32(bars);                                  // loader hand-off barriers (role 0)
+        for (int rel0 = 0; rel0 <= nproc; rel0 += RQ_STG) {
+#pragma unroll
+            for (int k = 0; k < RQ_STG; k++) {
+                const int rel = rel0 + k;
+                if (rel > nproc) break;
+                if (rel >= RQ_STG) {
+                    const int w = rel - RQ_STG;
+                    rq_mbar_wait(reinterpret_cast<unsigned long long *>(__cvta_shared_to_generic(lbase + 8u * (unsigned)(w & (RQ_RING - 1)))),
+                                 (unsigned)(w / RQ_RING) & 1u, w);
+                }
+                if (rel >= relA && rel < relB) {
+                    // order prior generic-proxy reads of this staging slot before the async-proxy writes
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb[k]), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dU[k]), "l"(gU), "r"(bU), "r"(fb[k]) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dV[k]), "l"(gV), "r"(bV), "r"(fb[k]) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dM[k]), "l"(gM), "r"(bM), "r"(fb[k]) : "memory");
+                } else {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb[k]) : "memory");
+                }
+                gU += PIT; gV += PIT; gM += PIT;
+            }
         }
     }
 }
