@@ -755,14 +755,28 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
     }
     const bool pressure_form = p->solver == FB_SOLVER_REDBLACK_PRESSURE;
     if (pressure_form) {
-        TJ = cdiv(cdiv(h->g.NY, cdiv(h->g.NY, RQ_TJ_MAX)), 16) * 16;
-        nstrips = cdiv(h->g.NY, TJ);
+        // pick strips x chunks: as many of the SMs as possible in ONE wave, least halo recomputation
+        const int lines = ie - ib;
+        double best = -1.0;
+        const int s_min = cdiv(h->g.NY, RQ_TJ_MAX);
+        for (int ns = s_min; ns <= s_min + 12; ns++) {
+            const int tj = cdiv(cdiv(h->g.NY, ns), 16) * 16;
+            if (tj > RQ_TJ_MAX || tj < 16) continue;
+            const int nstr = cdiv(h->g.NY, tj);
+            int nch = h->nsm / nstr; if (nch < 1) nch = 1;
+            const int max_chunks = cdiv(lines, 48);
+            if (nch > max_chunks) nch = max_chunks;
+            if (nch < 1) nch = 1;
+            const int ch = cdiv(lines, nch);
+            nch = cdiv(lines, ch);
+            const int ctas = nstr * nch;
+            const int waves = cdiv(ctas, h->nsm);
+            const double util = (double)ctas / (waves * h->nsm);
+            const double overhead = ((double)(tj + 2 * RQ_H + 16) / tj) * ((double)(ch + 2 * RQ_H) / ch);
+            const double score = util / overhead / waves;
+            if (score > best) { best = score; TJ = tj; nstrips = nstr; chunk = ch; nchunks = nch; }
+        }
         WL = TJ + 2 * RQ_H + 16;
-        nchunks = h->nsm / nstrips; if (nchunks < 1) nchunks = 1;
-        const int max_chunks = cdiv(ie - ib, 48);
-        if (nchunks > max_chunks) nchunks = max_chunks;
-        if (nchunks < 1) nchunks = 1;
-        chunk = cdiv(ie - ib, nchunks); nchunks = cdiv(ie - ib, chunk);
         if (!h->rbq_attr_set) {
             CK(cudaFuncSetAttribute(k_rbq_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CK(cudaFuncSetAttribute(k_rbq_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

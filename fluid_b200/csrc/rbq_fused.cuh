@@ -38,7 +38,8 @@
 #define RQ_NL 35          // line slots
 #define RQ_H 16
 #define RQ_THREADS 800
-#define RQ_TJ_MAX 416     // multiple of 16; WL = TJ + 48 <= 464 (16-byte granules for the TMA copies of the mask)
+#define RQ_TJ_MAX 464     // multiple of 16; WL = TJ + 48 <= 512 (a lane owns 2 groups of 4 cells per line;
+                          // 16-byte granules for the TMA copies of the mask)
 #define RQ_STG 4          // staging ring depth (lines in flight through TMA)
 // shared memory: 35 slots * WL * 9 B (q, -D0, neighbour count) + RQ_STG * (WL*9 + 16) B staging
 //                + hand-off mbarriers = 146.2 KB + 16.4 KB + 9.2 KB at WL = 464
