@@ -284,9 +284,15 @@ def main():
     dom_bytes = phase_alg_bytes.get(dom, 0) * cells_rank
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     proj_ms = phases["project"][0] / max(phases["project"][1], 1)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            traffic = json.load(fh).get(args.workload, {}).get(dom)
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "alg_bytes_per_cell": phase_alg_bytes.get(dom, 0), "ms_per_launch": dom_ms,
         "share_of_step": shares.get(dom, 0.0) / total_phase_ms,
         "step": {"alg_bytes_per_cell_step": bpc, "achieved": bpc * cells_rank / (ms / args.steps * 1e-3) / 1e9,
@@ -343,12 +349,14 @@ def main():
         # share of the Smoke() view D2H into pinned memory, min/max all-reduced
         import ctypes as C
         per = fluid_b200.edits.pack(preset.per_step)
-        mirror = sim.f._mirror(L.M)
+        # pinned buffer for this rank's slab only; fb_view addresses it as a window of the global array
+        slab = torch.empty(((sim.i_hi - sim.i_lo) * sim.NumY,), dtype=torch.float32, pin_memory=True)
+        view_base = slab.data_ptr() - sim.i_lo * sim.NumY * 4
         mn, mx = C.c_float(), C.c_float()
 
         def frame():
             sim.step(preset.dt, 1, per)
-            L.check(sim.f._h, L.lib.fb_view(sim.f._h, L.VIEW_SMOKE, mirror.ctypes.data, C.byref(mn), C.byref(mx)))
+            L.check(sim.f._h, L.lib.fb_view(sim.f._h, L.VIEW_SMOKE, view_base, C.byref(mn), C.byref(mx)))
             t = torch.tensor([-mn.value, mx.value], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
 
