@@ -14,16 +14,20 @@
 // checked bit for bit against its own CPU restatement fo_project_redblack_q.
 //
 // Structure: a CTA owns `chunk` lines x TJ columns (+16-cell halo, recomputed).  Lines
-// (constant i, contiguous in j) stream through a ring of 35 slots in 220 KB of shared
-// memory.  24 warps form a software pipeline WITHOUT block-wide barriers:
-//   thread 768   producer TMA bulk copies (cp.async.bulk + mbarrier) of the U, V, mask segments
-//                         of a line into a 4-deep staging ring, 4 lines ahead of the loader
-//   warps 16-19  loader   staging -> -D0, 1/s, q=0 in slot(L)
+// (constant i, contiguous in j) stream through a ring of 35 slots in shared memory.
+// 26 warps form a software pipeline WITHOUT block-wide barriers:
+//   thread 768   TMA producer for the loaders: cp.async.bulk of the U, V, mask segments of a
+//                line into an 6-deep staging ring (mbarrier complete_tx)
+//   thread 800   TMA producer for the writers: U0, V0, mask of the owned columns, 6-deep ring
+//   warps 16-19  loaders  warp 16+g takes lines == g (mod 4): staging -> -D0, neighbour count, q=0
 //   warp  s<16   half sweep s (colour s&1): may process line r once its predecessor
 //                (loader for s=0, warp s-1 otherwise) has finished line r+1
-//   warps 20-23  writer   slot(r), slot(r-1) + U0,V0 -> U,V,p in global     (register prefetch, 3 lines)
-// Each role publishes the last line it finished with st.release.cta and waits on its
-// predecessor with ld.acquire.cta; the loader reuses a slot once the writer is past it.
+//   warps 20-23  writers  warp 20+g takes owned lines == g (mod 4): slot(r), slot(r-1), staging
+//                -> U, V, p in global (STG.128)
+// Hand-offs are per-line mbarriers (arrive = release, try_wait = acquire); the loader reuses
+// a slot once the writers are past it.  Four lines are in flight in each of the serial
+// roles: ablation showed one iteration costing 264 us and eight 320 us, i.e. the sweeps
+// were hidden behind a one-line-at-a-time loader and writer.
 // Even and odd columns live in separate arrays so one colour is contiguous: a lane
 // updates 2 x 4 consecutive same-colour cells with LDS.128 / STS.128 and packed
 // FADD2 / FFMA2 (sm_100a fp32x2, bit-identical to the scalar operations).
@@ -37,16 +41,21 @@
 
 #define RQ_NL 35          // line slots
 #define RQ_H 16
-#define RQ_THREADS 800
-#define RQ_TJ_MAX 464     // multiple of 16; WL = TJ + 48 <= 512 (a lane owns 2 groups of 4 cells per line;
+#define RQ_THREADS 832
+#define RQ_TJ_MAX 448     // multiple of 16; WL = TJ + 48 <= 496 (a lane owns 2 groups of 4 cells per line;
                           // 16-byte granules for the TMA copies of the mask)
-#define RQ_STG 4          // staging ring depth (lines in flight through TMA)
-// shared memory: 35 slots * WL * 9 B (q, -D0, neighbour count) + RQ_STG * (WL*9 + 16) B staging
-//                + hand-off mbarriers = 146.2 KB + 16.4 KB + 9.2 KB at WL = 464
+#define RQ_STG 6          // loader staging ring depth (lines in flight through TMA)
+#define RQ_WSTG 6         // writer staging ring depth
+#define RQ_RING 64        // hand-off barriers per role (> RQ_NL, see rq_wait_line)
+#define RQ_ROLES 18
+// shared memory: 35 slots * WL * 9 B (q, -D0, neighbour count) + RQ_STG * (WL*9 + 16) B
+//                + RQ_WSTG * TJ*9 B + mbarriers = 156.2 + 26.9 + 24.2 + 9.3 KB at WL = 496
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
-__host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL)
+__host__ __device__ __forceinline__ size_t rq_wstage_bytes(int TJ) { return (size_t)TJ * 9; }
+__host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL, int TJ)
 {
-    return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + 8 * RQ_STG + 8 * 18 * 64 + 64;
+    return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + RQ_WSTG * rq_wstage_bytes(TJ) +
+           8 * (RQ_STG + RQ_WSTG) + 8 * RQ_ROLES * RQ_RING + 64;
 }
 
 struct RBQ {
@@ -223,8 +232,6 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const float *__r
 // Every role arrives for EVERY line 0 .. nproc in order, and no role can be more than
 // RQ_NL lines ahead of another (the loader waits for the slot), so with RQ_RING > RQ_NL a
 // parity wait always refers to the current or the immediately preceding phase.
-#define RQ_RING 64
-#define RQ_ROLES 18
 // Every lane arrives and every lane polls: measured faster than one arrive / one poller per
 // warp (lane-0 polling adds a divergent branch + __syncwarp to every hand-off: 0.35 -> 0.59 ms).
 __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line)
@@ -245,14 +252,19 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int WL = P.WL, WQ = WL >> 1, ROW = WL;             // elements per slot in one plane
+    const int TJ = P.TJ;
     float *sQ = reinterpret_cast<float *>(smem_raw);        // [slot][parity][q]
     float *sND = sQ + RQ_NL * WL;                            // -D0
     unsigned char *sC = reinterpret_cast<unsigned char *>(sND + RQ_NL * WL);   // fluid-neighbour count, 0 = never updated
-    // staging ring: per slot WL floats of U, WL+4 floats of V, WL mask bytes (raw global data)
+    // loader staging ring: per slot WL floats of U, WL+4 floats of V, WL mask bytes (raw global data)
     unsigned char *stg = sC + RQ_NL * WL;                    // 16-byte aligned: WL is a multiple of 16
     const int STG = (int)rq_stage_bytes(WL);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(stg + RQ_STG * STG);   // RQ_STG mbarriers
-    unsigned long long *bars = full + RQ_STG;                // RQ_ROLES * RQ_RING hand-off mbarriers
+    // writer staging ring: per slot TJ floats of U0, TJ floats of V0, TJ mask bytes (owned columns)
+    unsigned char *wstg = stg + RQ_STG * STG;
+    const int WSTG = (int)rq_wstage_bytes(TJ);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(wstg + RQ_WSTG * WSTG);   // RQ_STG mbarriers
+    unsigned long long *wfull = full + RQ_STG;               // RQ_WSTG mbarriers
+    unsigned long long *bars = wfull + RQ_WSTG;              // RQ_ROLES * RQ_RING hand-off mbarriers
 
     const Grid g = P.g;
     const int NX = g.NX, NY = g.NY, PIT = g.pitch;
@@ -261,17 +273,18 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     const int i0c = P.ib + blockIdx.y * P.chunk;
     const int i1c = min(i0c + P.chunk, P.ie);
     if (i0c >= i1c) return;
-    const int jr0 = strip * P.TJ - RQ_H;
+    const int jr0 = strip * TJ - RQ_H;
     const int e0 = i0c - RQ_H, e1 = i1c + RQ_H;               // half sweeps process lines [e0, e1); e1 is loaded too
     const int nst = P.nstages;
     const int nproc = e1 - e0;                                // lines each half sweep passes over
+    const int first_owned = i0c - e0, last_owned = (i1c - 1) - e0;   // relative lines the writers produce
 
     if (tid == 0) rq_debug = P.debug;
-    for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
-        const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);  // arrivals per phase = threads of the role
-    }
+    for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) rq_mbar_init(bars + k, 32);   // every role is one warp per line
     if (tid < RQ_STG) rq_mbar_init(full + tid, 1);
+    if (tid >= 32 && tid < 32 + RQ_WSTG) rq_mbar_init(wfull + (tid - 32), 1);
+    // the slot "below" line e0 (relative -1) must read as q = 0
+    for (int k = tid; k < WL; k += RQ_THREADS) sQ[(RQ_NL - 1) * ROW + k] = 0.0f;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -293,8 +306,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 const int slp = sl + 1 == RQ_NL ? 0 : sl + 1;
                 const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
                 const bool row_owned = (r >= i0c) && (r < i1c);
-                if (a) rq_line<1, STATS>(sQ, sND, sC, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, P.TJ, mymax, cy, have);
-                else   rq_line<0, STATS>(sQ, sND, sC, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, P.TJ, mymax, cy, have);
+                if (a) rq_line<1, STATS>(sQ, sND, sC, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, TJ, mymax, cy, have);
+                else   rq_line<0, STATS>(sQ, sND, sC, sl * ROW, slp * ROW, slm * ROW, WQ, lane, wd, row_owned, TJ, mymax, cy, have);
                 have = true;
             } else {
                 have = false;
@@ -309,63 +322,62 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 + s) >> 1), __float_as_uint(mymax));
         }
     } else if (warp < 20) {
-        // ================= loader: staging -> slot, lines e0 .. e1 =================
-        const int ld = tid - 512;
-        const bool active = ld < (WL >> 2);
-        const int j = jr0 + 4 * ld;
-        const bool col_in = active && j >= 0 && j < PIT;
-        if (active) {   // the slot "below" line e0 (relative -1) must read as q = 0
-            const int q = 2 * ld, b0 = (RQ_NL - 1) * ROW + q;
-            *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
-            *reinterpret_cast<float2 *>(sQ + b0 + WQ) = make_float2(0.f, 0.f);
-        }
-        int sl = 0;
-        const int last_owned = (i1c - 1) - e0;
-        for (int rel = 0; rel <= nproc; rel++) {
+        // ================= loaders: warp 16+g takes lines rel == g (mod 4), lines e0 .. e1 =================
+        const int grp = warp - 16;
+        const int ngroups = WL >> 2;                          // float4 column groups of a line
+        for (int rel = grp; rel <= nproc; rel += 4) {
             const int L = e0 + rel;
+            const int sl = rel % RQ_NL;
             // only interior lines inside this rank's slab hold updatable cells; line e1 is never swept
             const bool line_live = rel < nproc && L >= 1 && L <= NX - 2 && L >= g.i_alloc0 &&
                                    L + 1 < g.i_alloc0 + g.lines_alloc;
-            // slot(rel) last held line y-1 with y = rel-NL+1; its last readers work on line y: the writer
-            // if y is an owned line, otherwise the last half sweep
+            // slot(rel) last held line rel-NL; its last readers are the writers of lines rel-NL and rel-NL+1
+            // (owned lines) or the last half sweep working on line rel-NL+1 (halo lines)
             {
                 const int y = rel - RQ_NL + 1;
                 if (y >= 0) {
-                    if (y >= RQ_H && y <= last_owned) rq_wait_line(bars, 17, y);
-                    else rq_wait_line(bars, nst, y);
+                    if (y >= first_owned && y <= last_owned) {
+                        rq_wait_line(bars, 17, y);
+                        if (y - 1 >= first_owned) rq_wait_line(bars, 17, y - 1);
+                    } else {
+                        rq_wait_line(bars, nst, y);
+                        if (y - 1 >= first_owned && y - 1 <= last_owned) rq_wait_line(bars, 17, y - 1);
+                    }
                 }
             }
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            unsigned code = 0;
             if (rel < nproc) {
                 // lines rel and rel+1 must have landed (the producer stages every line 0 .. nproc)
                 rq_wait_warp(full + (rel % RQ_STG), (rel / RQ_STG) & 1, (30 << 20) | rel);
                 rq_wait_warp(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1, (31 << 20) | rel);
             }
-            if (line_live && col_in) {
-                const unsigned char *s0 = stg + (rel % RQ_STG) * STG, *s1 = stg + ((rel + 1) % RQ_STG) * STG;
-                const float *stU = reinterpret_cast<const float *>(s0), *stV = stU + WL;
-                const float *stU1 = reinterpret_cast<const float *>(s1);
-                const unsigned char *stM = s0 + (size_t)(2 * WL + 4) * 4;
-                float u0[4], u1[4], v[5];
-                unpack(*reinterpret_cast<const float4 *>(stU + 4 * ld), u0);
-                unpack(*reinterpret_cast<const float4 *>(stU1 + 4 * ld), u1);
-                unpack(*reinterpret_cast<const float4 *>(stV + 4 * ld), v);
-                v[4] = (j + 4 < PIT) ? stV[4 * ld + 4] : 0.0f;
-                const unsigned mk = *reinterpret_cast<const unsigned *>(stM + 4 * ld);
+            const unsigned char *s0 = stg + (rel % RQ_STG) * STG, *s1 = stg + ((rel + 1) % RQ_STG) * STG;
+            const float *stU = reinterpret_cast<const float *>(s0), *stV = stU + WL;
+            const float *stU1 = reinterpret_cast<const float *>(s1);
+            const unsigned char *stM = s0 + (size_t)(2 * WL + 4) * 4;
+#pragma unroll 4
+            for (int gi = lane; gi < ngroups; gi += 32) {
+                const int j = jr0 + 4 * gi;
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                unsigned code = 0;
+                if (line_live && j >= 0 && j < PIT) {
+                    float u0[4], u1[4], v[5];
+                    unpack(*reinterpret_cast<const float4 *>(stU + 4 * gi), u0);
+                    unpack(*reinterpret_cast<const float4 *>(stU1 + 4 * gi), u1);
+                    unpack(*reinterpret_cast<const float4 *>(stV + 4 * gi), v);
+                    v[4] = (j + 4 < PIT) ? stV[4 * gi + 4] : 0.0f;
+                    const unsigned mk = *reinterpret_cast<const unsigned *>(stM + 4 * gi);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const unsigned m = (mk >> (8 * k)) & 0xffu;
-                    const int jj = j + k;
-                    const unsigned ns = __popc(m & 30u);
-                    const bool upd = (m & MK_C) && ns > 0 && jj >= 1 && jj <= NY - 2;
-                    const float dv = ((u1[k] - u0[k]) + v[k + 1]) - v[k];
-                    d[k] = upd ? -dv : 0.0f;
-                    if (upd) code |= ns << (8 * k);
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned m = (mk >> (8 * k)) & 0xffu;
+                        const int jj = j + k;
+                        const unsigned ns = __popc(m & 30u);
+                        const bool upd = (m & MK_C) && ns > 0 && jj >= 1 && jj <= NY - 2;
+                        const float dv = ((u1[k] - u0[k]) + v[k + 1]) - v[k];
+                        d[k] = upd ? -dv : 0.0f;
+                        if (upd) code |= ns << (8 * k);
+                    }
                 }
-            }
-            if (active) {
-                const int q = 2 * ld;
+                const int q = 2 * gi;
                 const int b0 = sl * ROW + q, b1 = b0 + WQ;
                 *reinterpret_cast<float2 *>(sND + b0) = make_float2(d[0], d[2]);
                 *reinterpret_cast<float2 *>(sND + b1) = make_float2(d[1], d[3]);
@@ -374,46 +386,38 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 *reinterpret_cast<unsigned short *>(sC + b0) = (unsigned short)((code & 0xffu) | ((code >> 8) & 0xff00u));
                 *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)(((code >> 8) & 0xffu) | ((code >> 16) & 0xff00u));
             }
-            rq_done(bars, 0, rel);                            // one arrive per loader warp
-            sl = sl + 1 == RQ_NL ? 0 : sl + 1;
+            rq_done(bars, 0, rel);
         }
     } else if (warp < 24) {
-        // ================= writer: owned lines -> U, V, p =================
-        const int st = tid - 640;
-        const bool active = st < (P.TJ >> 2);
-        const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
-        const bool col_ok = active && w_j < NY;
-        struct WIn { float4 u, v, p; unsigned m; };
-        WIn in[3];
-        auto wfetch = [&](int r, WIn &x) {
-            x.u = x.v = x.p = make_float4(0.f, 0.f, 0.f, 0.f);
-            x.m = 0;
-            if (!col_ok || r < i0c || r >= i1c) return;
-            const int o = (r - g.i_alloc0) * PIT + w_j;
-            x.u = ld4(P.U + o);
-            x.v = ld4(P.V + o);
-            x.m = __ldg(reinterpret_cast<const unsigned *>(P.mask + o));
-            if (P.Pin) x.p = ld4(P.Pin + o);
-        };
-        // only owned lines are written, but the hand-off phases count every line: arrive for the halo lines first
-        for (int rel = 0; rel < i0c - e0; rel++) rq_done(bars, 17, rel);
-        // 3 lines of inputs are kept in flight
-        wfetch(i0c, in[0]); wfetch(i0c + 1, in[1]); wfetch(i0c + 2, in[2]);
-        int sl = (i0c - e0) % RQ_NL;
-        for (int r0 = i0c; r0 < i1c; r0 += 3) {
-#pragma unroll
-            for (int kk = 0; kk < 3; kk++) {
-                const int r = r0 + kk;
-                if (r >= i1c) break;
-                const int rel = r - e0;
-                rq_wait_line(bars, nst, rel);                 // last half sweep is past line r
-                if (col_ok && !(P.xflags & 2)) {
+        // ================= writers: warp 20+g takes owned lines rel == g (mod 4) =================
+        const int grp = warp - 20;
+        const int ngroups = TJ >> 2;
+        // the hand-off phases count every line: arrive for the halo lines this warp would have taken
+        for (int rel = grp; rel < first_owned; rel += 4) rq_done(bars, 17, rel);
+        int rel = first_owned + ((grp - first_owned) & 3);
+        for (; rel <= last_owned; rel += 4) {
+            const int r = e0 + rel;
+            const int n = rel - first_owned;                  // n-th owned line: writer staging slot n % RQ_WSTG
+            rq_wait_warp(wfull + (n % RQ_WSTG), (n / RQ_WSTG) & 1, (29 << 20) | rel);
+            rq_wait_line(bars, nst, rel);                     // last half sweep is past line r
+            if (!(P.xflags & 2)) {
+                const int sl = rel % RQ_NL, slm = (rel + RQ_NL - 1) % RQ_NL;
+                const unsigned char *w0 = wstg + (n % RQ_WSTG) * WSTG;
+                const float *wU = reinterpret_cast<const float *>(w0), *wV = wU + TJ;
+                const unsigned char *wM = w0 + (size_t)TJ * 8;
+                const bool line_first = (r == 0);
+                const bool turb_line = P.turb > 0.0f && r >= 1 && r <= NX - 2;
+#pragma unroll 2
+                for (int gi = lane; gi < ngroups; gi += 32) {
+                    const int w_lj = RQ_H + 4 * gi, w_j = jr0 + w_lj;
+                    if (w_j >= NY) continue;
                     const int o = (r - g.i_alloc0) * PIT + w_j;
-                    const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
                     const int q = w_lj >> 1;
-                    float u[4], v[4], pin[4], qc[4], qx[4], ql;
-                    unpack(in[kk].u, u); unpack(in[kk].v, v); unpack(in[kk].p, pin);
-                    const unsigned m4 = in[kk].m;
+                    float u[4], v[4], pin[4] = {0.f, 0.f, 0.f, 0.f}, qc[4], qx[4], ql;
+                    unpack(*reinterpret_cast<const float4 *>(wU + 4 * gi), u);
+                    unpack(*reinterpret_cast<const float4 *>(wV + 4 * gi), v);
+                    const unsigned m4 = *reinterpret_cast<const unsigned *>(wM + 4 * gi);
+                    if (P.Pin) unpack(ld4(P.Pin + o), pin);
                     {
                         const float2 ev = *reinterpret_cast<const float2 *>(sQ + sl * ROW + q);
                         const float2 od = *reinterpret_cast<const float2 *>(sQ + sl * ROW + WQ + q);
@@ -423,8 +427,6 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                         qx[0] = evm.x; qx[1] = odm.x; qx[2] = evm.y; qx[3] = odm.y;
                         ql = sQ[sl * ROW + WQ + q - 1];                  // column lj-1 (odd parity, index q-1)
                     }
-                    wfetch(r + 3, in[kk]);
-                    const bool line_first = (r == 0);
                     float pu[4], pv[4], pp[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -438,9 +440,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                         const float b2 = ((m & MK_C) && (w_j + k) > 0) ? qym : 0.0f;
                         const float t2 = v[k] - a2;
                         pv[k] = t2 + b2;
-                        pp[k] = __fmaf_rn(P.cp, qc[k], P.Pin ? pin[k] : 0.0f);
+                        pp[k] = __fmaf_rn(P.cp, qc[k], pin[k]);
                     }
-                    if (P.turb > 0.0f && r >= 1 && r <= NX - 2) {        // fused addTurbulence (fluid.go:496-526)
+                    if (turb_line) {                                     // fused addTurbulence (fluid.go:496-526)
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const unsigned m = (m4 >> (8 * k)) & 0xffu;
@@ -463,61 +465,77 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                     store4(P.Vo + o, NY, w_j, pv);
                     store4(P.Po + o, NY, w_j, pp);
                 }
-                rq_done(bars, 17, rel);                       // one arrive per writer warp
-                sl = sl + 1 == RQ_NL ? 0 : sl + 1;
             }
+            rq_done(bars, 17, rel);
         }
     } else if (tid == 768) {
-        // ================= producer: TMA bulk copies into the staging ring =================
-        // line rel goes to staging slot rel % RQ_STG once the loader is past line rel - RQ_STG
-        // (the loader reads staging slot(rel) for lines rel-1 and rel).  One thread: everything
-        // that does not change from line to line is hoisted, the loop body is ~30 instructions.
+        // ================= producer for the loaders: TMA bulk copies into the staging ring =================
+        // line rel goes to staging slot rel % RQ_STG once the loaders of lines rel-RQ_STG and
+        // rel-RQ_STG-1 are done (slot(x) is read for lines x-1 and x).
         const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
         const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
         const int off = cj0 - jr0;                                            // staging column of global column cj0
         const unsigned bU = (unsigned)(cjU - cj0) * 4, bV = (unsigned)(cjV - cj0) * 4, bM = (unsigned)(cjU - cj0);
         const unsigned bytes = bU + bV + bM;
-        // lines that exist in this rank's planes: relative [relA, relB)
         const int lineA = max(0, g.i_alloc0), lineB = min(NX, g.i_alloc0 + g.lines_alloc);
         const int relA = lineA - e0, relB = (cjU > cj0 && !(P.xflags & 4)) ? lineB - e0 : -1;
-        unsigned dU[RQ_STG], dV[RQ_STG], dM[RQ_STG], fb[RQ_STG];
-#pragma unroll
-        for (int k = 0; k < RQ_STG; k++) {
-            unsigned char *s0 = stg + k * STG;
-            dU[k] = rq_s32(reinterpret_cast<float *>(s0) + off);
-            dV[k] = rq_s32(reinterpret_cast<float *>(s0) + WL + off);
-            dM[k] = rq_s32(s0 + (size_t)(2 * WL + 4) * 4 + off);
-            fb[k] = rq_s32(full + k);
-        }
         const long long o0 = (long long)(e0 - g.i_alloc0) * PIT + cj0;       // offset of relative line 0 (may be negative)
         const float *gU = P.U + o0, *gV = P.V + o0;
         const unsigned char *gM = P.mask + o0;
-        const unsigned lbase = rq_s32(bars);                                  // loader hand-off barriers (role 0)
-        for (int rel0 = 0; rel0 <= nproc; rel0 += RQ_STG) {
-#pragma unroll
-            for (int k = 0; k < RQ_STG; k++) {
-                const int rel = rel0 + k;
-                if (rel > nproc) break;
-                if (rel >= RQ_STG) {
-                    const int w = rel - RQ_STG;
-                    rq_mbar_wait(reinterpret_cast<unsigned long long *>(__cvta_shared_to_generic(lbase + 8u * (unsigned)(w & (RQ_RING - 1)))),
-                                 (unsigned)(w / RQ_RING) & 1u, w);
-                }
-                if (rel >= relA && rel < relB) {
-                    // order prior generic-proxy reads of this staging slot before the async-proxy writes
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb[k]), "r"(bytes) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dU[k]), "l"(gU), "r"(bU), "r"(fb[k]) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dV[k]), "l"(gV), "r"(bV), "r"(fb[k]) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dM[k]), "l"(gM), "r"(bM), "r"(fb[k]) : "memory");
-                } else {
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb[k]) : "memory");
-                }
-                gU += PIT; gV += PIT; gM += PIT;
+        for (int rel = 0; rel <= nproc; rel++) {
+            const int k = rel % RQ_STG;
+            if (rel >= RQ_STG) {
+                rq_wait_line(bars, 0, rel - RQ_STG);
+                if (rel - RQ_STG - 1 >= 0) rq_wait_line(bars, 0, rel - RQ_STG - 1);
             }
+            unsigned char *s0 = stg + k * STG;
+            const unsigned fb = rq_s32(full + k);
+            if (rel >= relA && rel < relB) {
+                const unsigned dU = rq_s32(reinterpret_cast<float *>(s0) + off);
+                const unsigned dV = rq_s32(reinterpret_cast<float *>(s0) + WL + off);
+                const unsigned dM = rq_s32(s0 + (size_t)(2 * WL + 4) * 4 + off);
+                // order prior generic-proxy reads of this staging slot before the async-proxy writes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dU), "l"(gU), "r"(bU), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dV), "l"(gV), "r"(bV), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dM), "l"(gM), "r"(bM), "r"(fb) : "memory");
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+            }
+            gU += PIT; gV += PIT; gM += PIT;
+        }
+    } else if (tid == 800) {
+        // ================= producer for the writers: U0, V0, mask of the owned columns =================
+        const int c0 = strip * TJ;                                            // first owned column (multiple of 16)
+        const int c1 = min(c0 + TJ, PIT);
+        const bool any = c1 > c0 && !(P.xflags & 2);
+        const unsigned bF = any ? (unsigned)(c1 - c0) * 4 : 0, bM = any ? (unsigned)(c1 - c0) : 0;
+        const size_t o0 = (size_t)(i0c - g.i_alloc0) * PIT + c0;
+        const float *gU = P.U + o0, *gV = P.V + o0;
+        const unsigned char *gM = P.mask + o0;
+        const int nown = i1c - i0c;
+        for (int n = 0; n < nown; n++) {
+            const int k = n % RQ_WSTG;
+            if (n >= RQ_WSTG) rq_wait_line(bars, 17, first_owned + n - RQ_WSTG);   // that writer is done with the slot
+            unsigned char *w0 = wstg + k * WSTG;
+            const unsigned fb = rq_s32(wfull + k);
+            if (any) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(2 * bF + bM) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(rq_s32(w0)), "l"(gU), "r"(bF), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(rq_s32(w0 + (size_t)TJ * 4)), "l"(gV), "r"(bF), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(rq_s32(w0 + (size_t)TJ * 8)), "l"(gM), "r"(bM), "r"(fb) : "memory");
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+            }
+            gU += PIT; gV += PIT; gM += PIT;
         }
     }
 }

@@ -1,15 +1,20 @@
-import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
-import numpy as np, fluid_b200, oracle
-from fluid_b200 import presets
-from common import apply_preset, copy_state, diff_report
-for size, iters in (((200,120),1), ((200,120),8), ((520,75),8), ((2048,2048),8)):
-    p = presets.karman(*size)
-    g = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
-    apply_preset(g, p); g.edit(p.per_step)
-    t=time.time()
-    try:
-        g.makeIncompressible(iters, p.dt); g.synchronize(); print(size, iters, "ok", round(time.time()-t,3), g.solve_stats()["max_div"][-1])
-    except Exception as e:
-        print(size, iters, "ERR", round(time.time()-t,3), e)
-    g.close()
+"""Ablation timing of the fused pressure solve (FLUIDB200_RBQ_X bits: 1 skip sweeps, 2 skip writer I/O, 4 skip TMA)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fluid_b200
+from fluid_b200 import presets, _lib as L
+
+p = presets.jet(4096, 4096)
+g = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
+g.edit(p.init); g.step(p.dt, 5, p.per_step); g.edit(p.per_step)
+g.set_option(L.OPT_SOLVE_STATS, 0)
+for iters in (1, 2, 4, 8):
+    for _ in range(3):
+        g.makeIncompressible(iters, p.dt)
+    g.synchronize()
+    g.timer_start()
+    for _ in range(10):
+        g.makeIncompressible(iters, p.dt)
+    ms = g.timer_stop() / 10
+    print(f"x={os.environ.get('FLUIDB200_RBQ_X','0')} iters={iters} nstages={2*iters}: {ms*1000:.1f} us")
+g.close()
