@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfluidb200.so")
+# FLUIDB200_LIB: load another build of the SAME library (kernel experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("FLUIDB200_LIB") or os.path.join(_HERE, "libfluidb200.so")
 
 FB_OK = 0
 STATUS = {0: "FB_OK", -1: "FB_ERR_INVALID", -2: "FB_ERR_CUDA", -3: "FB_ERR_NOMEM",

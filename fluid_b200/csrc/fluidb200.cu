@@ -807,7 +807,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             volatile float ts = p->turbulence_strength * dt;
             a.noiseU = nU; a.noiseV = nV; a.turb = ts;
         }
-        const size_t smem_q = rq_smem_bytes(WL, TJ);   // planes + two TMA staging rings + mbarriers
+        const size_t smem_q = rq_smem_bytes(WL, TJ);   // planes + TMA staging ring + mbarriers + progress counters
         if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
         else k_rbq_fused<false><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
         CKL("k_rbq_fused");
