@@ -13,7 +13,9 @@ value     device-resident: inputs live in HBM, K steps timed with CUDA events on
           library's stream between barriers + synchronizes, max over ranks.
 e2e       the frame loop a user of the Go API runs: per step the edit commands go
           host->device, Simulate runs, and the Smoke() view (field + min/max) comes
-          back device->host into pinned memory (main/main.go Update + Draw).
+          back device->host into pinned memory (main/main.go Update + Draw), pipelined
+          with fb_view_begin/end so that frame k's transfer overlaps Simulate k+1; the
+          blocking variant of the same loop is reported beside it.
 roofline  dominant phase of the step (largest share of device time, measured with CUDA
           events per phase inside the timed region) against the measured HBM peak.
 cpu_baseline  oracle/ (C restatement of the Go reference, all host threads) on a bounded
@@ -337,14 +339,34 @@ def main():
         for _ in range(args.steps):
             frame()
         barrier()
+        sync_s = time.perf_counter() - t0
+
+        # the same loop pipelined: frame k's view travels to the host while Simulate k+1 runs
+        # (fb_view_begin / fb_view_end, two pinned frame buffers -- the renderer reads one while
+        # the other fills).  Every step's view still reaches host memory inside the timed region.
+        frames = [torch.empty((sim.NumX * sim.NumY,), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+
+        def pipelined(n):
+            sim.step(preset.dt, 1, per)
+            sim.view_begin(L.VIEW_SMOKE, frames[0].data_ptr())
+            for k in range(1, n):
+                sim.step(preset.dt, 1, per)
+                sim.view_end()
+                sim.view_begin(L.VIEW_SMOKE, frames[k & 1].data_ptr())
+            return sim.view_end()
+
+        pipelined(3)
+        barrier()
+        t0 = time.perf_counter()
+        pipelined(args.steps)
+        barrier()
         e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
         e2e = {"value": cells_total * args.steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(sim.NumX * sim.NumY * 4 + 8), "ms_per_step": e2e_s / args.steps * 1e3,
-               "what": "per step: edit commands H2D, Simulate, Smoke() view (field + min/max) D2H into pinned memory"}
+               "what": "per step: edit commands H2D, Simulate, Smoke() view (field + min/max) D2H into pinned memory; "
+                       "pipelined frame loop (fb_view_begin/end): the view of step k travels while step k+1 computes",
+               "blocking_loop": {"value": cells_total * args.steps / sync_s, "ms_per_step": sync_s / args.steps * 1e3,
+                                 "what": "same loop with the blocking fb_view after every step"}}
 
         # ---- the other solver on the same workload (reported, not the headline)
         other = fluid_b200.SOLVER_EXACT if solver != fluid_b200.SOLVER_EXACT else fluid_b200.SOLVER_REDBLACK_PRESSURE
@@ -367,18 +389,27 @@ def main():
         view_base = slab.data_ptr() - sim.i_lo * sim.NumY * 4
         mn, mx = C.c_float(), C.c_float()
 
-        def frame():
-            sim.step(preset.dt, 1, per)
-            L.check(sim.f._h, L.lib.fb_view(sim.f._h, L.VIEW_SMOKE, view_base, C.byref(mn), C.byref(mx)))
-            t = torch.tensor([-mn.value, mx.value], device="cuda")
+        # pipelined frame loop (see the single-GPU leg): two pinned slab buffers per rank
+        slabs = [slab, torch.empty_like(slab).pin_memory()]
+        bases = [b.data_ptr() - sim.i_lo * sim.NumY * 4 for b in slabs]
+
+        def reduce_minmax(mm):
+            t = torch.tensor([-mm[0], mm[1]], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
 
-        for _ in range(3):
-            frame()
+        def pipelined(n):
+            sim.step(preset.dt, 1, per)
+            sim.f.view_begin(L.VIEW_SMOKE, bases[0])
+            for k in range(1, n):
+                sim.step(preset.dt, 1, per)
+                reduce_minmax(sim.f.view_end())
+                sim.f.view_begin(L.VIEW_SMOKE, bases[k & 1])
+            reduce_minmax(sim.f.view_end())
+
+        pipelined(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            frame()
+        pipelined(args.steps)
         barrier()
         t = torch.tensor([time.perf_counter() - t0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -386,7 +417,7 @@ def main():
         e2e = {"value": cells_total * args.steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(per.nbytes) * world,
                "d2h_bytes_per_step": int(cells_total * 4 + 8 * world), "ms_per_step": e2e_s / args.steps * 1e3,
                "what": "per step and rank: edit commands H2D, slab Simulate + halo exchange, slab of the Smoke() view D2H "
-                       "into pinned memory, min/max all-reduce"}
+                       "into pinned memory, min/max all-reduce; pipelined frame loop (fb_view_begin/end)"}
 
     # residual actually reached by the headline solver on the final state
     st = sim.solve_stats() if hasattr(sim, "solve_stats") else {}

@@ -68,6 +68,8 @@ SYMBOLS = {
     "fb_download": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "fb_host_mirror": (C.c_int, [_H, C.c_int32, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]),
     "fb_view": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fb_view_begin": (C.c_int, [_H, C.c_int32, C.c_void_p]),
+    "fb_view_end": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fb_reduce": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_float)]),
     "fb_sample_velocity": (C.c_int, [_H, C.c_size_t, C.c_void_p, C.c_void_p]),
     "fb_halo_region": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -16,7 +16,7 @@
 
 #define FB_VERSION 100
 
-enum { SCR_CURL = 0, SCR_A, SCR_B, SCR_C, SCR_D, SCR_E, SCR_F, SCR_BKU, SCR_BKV, SCR_NOISEU, SCR_NOISEV, SCR_VIEW, SCR_N };
+enum { SCR_CURL = 0, SCR_A, SCR_B, SCR_C, SCR_D, SCR_E, SCR_F, SCR_BKU, SCR_BKV, SCR_NOISEU, SCR_NOISEV, SCR_VIEW, SCR_SNAP, SCR_N };
 
 struct fb_handle {
     fb_config cfg;
@@ -47,6 +47,9 @@ struct fb_handle {
     fb_edit_cmd *d_cmds; size_t d_cmds_cap;
     std::vector<fb_edit_cmd> staged_cmds;   // host copy of what d_cmds holds (per-step lists repeat)
     cudaEvent_t ev0, ev1;
+    cudaStream_t copy_stream;     // device -> host leg of asynchronous views
+    cudaEvent_t ev_snap, ev_view; // snapshot taken / view landed in host memory
+    bool view_in_flight;
     bool prof;
     std::vector<cudaEvent_t> prof_pool;                 // recycled events
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pairs;
@@ -226,6 +229,9 @@ extern "C" int fb_destroy(fb_handle *h)
     for (auto e : h->prof_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    if (h->ev_view) cudaEventDestroy(h->ev_view);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return FB_OK;
@@ -1344,6 +1350,71 @@ extern "C" int fb_view(fb_handle *h, int32_t kind, float *out, float *min_value,
                              (size_t)(g.i_hi - g.i_lo), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    if (min_value) *min_value = key2f(h->h_red[32]);
+    if (max_value) *max_value = key2f(h->h_red[33]);
+    return FB_OK;
+}
+
+// Pipelined view: the snapshot and the reduction are queued behind the work already on the
+// handle's stream, the transfer runs on a second stream, and the call returns at once.  A frame
+// loop calls fb_view_begin(k), queues Simulate k+1, then fb_view_end(k): the PCIe transfer of
+// frame k overlaps the computation of frame k+1 (main/main.go draws frame k meanwhile).
+extern "C" int fb_view_begin(fb_handle *h, int32_t kind, float *out)
+{
+    if (!h || !out) return FB_ERR_INVALID;
+    if (h->view_in_flight) return fail(h, FB_ERR_INVALID, "fb_view_begin: a view is already in flight");
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_view, cudaEventDisableTiming));
+    }
+    float *snap;
+    TRY(scratch(h, SCR_SNAP, &snap));
+    k_minmax_init<<<1, 1, 0, h->stream>>>(h->d_red + 32);
+    CKL("k_minmax_init");
+    const float *src = nullptr;
+    int reduce = 1;
+    switch (kind) {
+    case FB_VIEW_SMOKE: src = h->f[FB_M]; break;
+    case FB_VIEW_PRESSURE: src = h->f[FB_P]; break;
+    case FB_VIEW_VELOCITY_MAGNITUDE: case FB_VIEW_VORTICITY: {
+        float *view;
+        TRY(scratch(h, SCR_VIEW, &view));
+        if (kind == FB_VIEW_VORTICITY)
+            k_view<FB_VIEW_VORTICITY><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        else
+            k_view<FB_VIEW_VELOCITY_MAGNITUDE><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        CKL("k_view");
+        src = view;
+        reduce = 0;          // k_view already reduced over the fluid interior (Q-14)
+        break;
+    }
+    default: return fail(h, FB_ERR_INVALID, "unknown view");
+    }
+    k_snapshot_minmax<<<grid, block, 0, h->stream>>>(g, src, snap, h->d_red + 32, ib, ie, reduce);
+    CKL("k_snapshot_minmax");
+    CK(cudaEventRecord(h->ev_snap, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    CK(cudaMemcpyAsync(out + (size_t)ib * g.NY, snap, (size_t)(ie - ib) * g.NY * sizeof(float), cudaMemcpyDeviceToHost,
+                       h->copy_stream));
+    CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(h->ev_view, h->copy_stream));
+    // the next kernel that touches d_red[32..33] or the snapshot is the next fb_view_begin, after fb_view_end
+    h->view_in_flight = true;
+    return FB_OK;
+}
+
+extern "C" int fb_view_end(fb_handle *h, float *min_value, float *max_value)
+{
+    if (!h) return FB_ERR_INVALID;
+    if (!h->view_in_flight) return fail(h, FB_ERR_INVALID, "fb_view_end: no view in flight");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev_view));
+    h->view_in_flight = false;
     if (min_value) *min_value = key2f(h->h_red[32]);
     if (max_value) *max_value = key2f(h->h_red[33]);
     return FB_OK;

@@ -607,6 +607,29 @@ __global__ void k_minmax_all(Grid g, const float *__restrict__ A, unsigned *red,
     block_minmax(lo, hi, red);
 }
 
+// Asynchronous views: sentinels of the min/max pair without a host copy, and a compact
+// (pitch -> NumY) snapshot of lines [ib, ie) fused with the min/max pass, so that the device
+// to host copy is ONE contiguous transfer that may overlap the next Simulate.
+__global__ void k_minmax_init(unsigned *red)
+{
+    red[0] = f2key(3.402823466e+38f);
+    red[1] = f2key(-3.402823466e+38f);
+}
+__global__ void k_snapshot_minmax(Grid g, const float *__restrict__ A, float *__restrict__ snap, unsigned *red,
+                                  int ib, int ie, int reduce)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = ib + blockIdx.y * blockDim.y + threadIdx.y;
+    float lo = 3.402823466e+38f, hi = -3.402823466e+38f;
+    if (i < ie && j < g.NY) {
+        const float v = A[g.at(i, j)];
+        snap[(size_t)(i - ib) * g.NY + j] = v;
+        if (v < lo) lo = v;
+        if (v > hi) hi = v;
+    }
+    if (reduce) block_minmax(lo, hi, red);
+}
+
 // Vorticity (fluid.go:806-838) / VelocityMagnitude (fluid.go:841-873)
 template <int KIND>
 __global__ void k_view(Grid g, const float *__restrict__ U, const float *__restrict__ V,

@@ -343,6 +343,20 @@ class Fluid:
         L.check(self._h, L.lib.fb_view(self._h, kind, out.ctypes.data, C.byref(mn), C.byref(mx)))
         return ScalarField(out, mn.value, mx.value)
 
+    def view_begin(self, kind: int, out) -> None:
+        """Pipelined view (fb_view_begin): queue the view behind the submitted work and return.
+        ``out`` is a pinned float32 host array of the dense global shape (or its address); the
+        transfer overlaps whatever is queued next.  Pair with view_end()."""
+        self.flush()
+        addr = out if isinstance(out, int) else out.ctypes.data
+        L.check(self._h, L.lib.fb_view_begin(self._h, kind, addr))
+
+    def view_end(self):
+        """Wait for the view started by view_begin(); returns (min, max)."""
+        mn, mx = C.c_float(), C.c_float()
+        L.check(self._h, L.lib.fb_view_end(self._h, C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
     def Smoke(self) -> ScalarField:               # smoke.go:5
         return self._view(L.VIEW_SMOKE)
 

@@ -67,6 +67,8 @@ type Fluid struct {
 	numCells int
 	pending  []C.fb_edit_cmd // edits queued since the last flush
 	solidOK  bool            // the S mirror reflects every edit issued so far
+	frame    int             // which pinned frame buffer the view in flight targets (BeginSmoke)
+	frameBuf []float32
 }
 
 func check(h *C.fb_handle, st C.int) {
@@ -303,6 +305,34 @@ func (f *Fluid) view(kind C.int32_t) ScalarField {
 
 // Smoke replaces smoke.go:5-24.
 func (f *Fluid) Smoke() ScalarField { return f.view(C.FB_VIEW_SMOKE) }
+
+// BeginSmoke / EndSmoke are the pipelined form of Smoke() for a frame loop (fb_view_begin /
+// fb_view_end): BeginSmoke queues the view behind the Simulate calls already made and returns
+// at once; the frame travels to the host while the next Simulate runs; EndSmoke waits for it.
+// The two frame buffers are the library's pinned mirrors of M and newM (C-owned memory, so the
+// asynchronous copy never touches Go memory); a frame stays valid until the next-but-one BeginSmoke.
+//
+//	f.Simulate(dt); f.BeginSmoke()
+//	for { f.Simulate(dt); frame := f.EndSmoke(); f.BeginSmoke(); draw(frame) }
+func (f *Fluid) BeginSmoke() {
+	f.flush()
+	f.frame ^= 1
+	field := C.int32_t(C.FB_M)
+	if f.frame == 1 {
+		field = C.int32_t(C.FB_NEWM)
+	}
+	var ptr *C.float
+	var n C.size_t
+	check(f.h, C.fb_host_mirror(f.h, field, &ptr, &n))
+	f.frameBuf = unsafe.Slice((*float32)(unsafe.Pointer(ptr)), int(n))
+	check(f.h, C.fb_view_begin(f.h, C.FB_VIEW_SMOKE, ptr))
+}
+
+func (f *Fluid) EndSmoke() ScalarField {
+	var mn, mx C.float
+	check(f.h, C.fb_view_end(f.h, &mn, &mx))
+	return ScalarField{NumX: f.NumX, NumY: f.NumY, values: f.frameBuf, MinValue: float32(mn), MaxValue: float32(mx)}
+}
 
 // Pressure replaces pressure.go:5-24.
 func (f *Fluid) Pressure() ScalarField { return f.view(C.FB_VIEW_PRESSURE) }

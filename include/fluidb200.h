@@ -193,6 +193,13 @@ int fb_host_mirror(fb_handle *h, int32_t field, float **ptr, size_t *count);
 
 /* ---- views and reductions (Q-14 semantics) ------------------------------ */
 int fb_view(fb_handle *h, int32_t kind, float *out_or_null, float *min_value, float *max_value);
+/* Pipelined form of fb_view for a frame loop: `begin` queues the view behind the work already
+ * submitted and returns at once; the transfer into `out` (pinned host memory, dense global
+ * layout) runs on a second stream and overlaps whatever is queued next (the next Simulate);
+ * `end` waits for it and returns min / max.  One view may be in flight per handle.  This is
+ * main/main.go's draw-frame-k-while-computing-k+1 loop: Smoke() at main/main.go:247. */
+int fb_view_begin(fb_handle *h, int32_t kind, float *out);
+int fb_view_end(fb_handle *h, float *min_value, float *max_value);
 int fb_reduce(fb_handle *h, int32_t kind, float *out);
 /* SampleVelocity (fluid.go:799-803) for n points; xy and uv are [n][2]. */
 int fb_sample_velocity(fb_handle *h, size_t n, const float *xy, float *uv);

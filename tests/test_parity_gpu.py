@@ -321,6 +321,33 @@ def test_views_and_reductions_match():
     g.close()
 
 
+def test_pipelined_view_equals_blocking_view_and_overlaps_next_step():
+    """fb_view_begin / fb_view_end: the frame that lands in host memory is the state at the time of
+    `begin`, even though a Simulate is queued behind it before `end`; min / max as fb_view."""
+    import fluid_b200
+    from fluid_b200 import presets, _lib as L
+    p = presets.karman(150, 90)
+    o = developed_state(p)
+    g = gpu_clone(o, p)
+    kinds = {"Smoke": L.VIEW_SMOKE, "Pressure": L.VIEW_PRESSURE, "VelocityMagnitude": L.VIEW_VELOCITY_MAGNITUDE,
+             "Vorticity": L.VIEW_VORTICITY}
+    for name, kind in kinds.items():
+        want = getattr(o, name)()
+        out = np.full((g.NumX, g.NumY), np.nan, dtype=np.float32)
+        g.view_begin(kind, out)
+        with pytest.raises(fluid_b200.FluidError):
+            g.view_begin(kind, out)                      # one view in flight per handle
+        g.step(p.dt, 1, p.per_step)                      # overwrites M / U / V / p behind the snapshot
+        mn, mx = g.view_end()
+        assert_bit_exact(name, out, want.values)
+        assert np.float32(mn) == np.float32(want.MinValue) and np.float32(mx) == np.float32(want.MaxValue), name
+        o.edit(p.per_step); o.Simulate(p.dt)
+    with pytest.raises(fluid_b200.FluidError):
+        g.view_end()                                     # nothing in flight
+    assert_bit_exact("Smoke after", g.Smoke().values, o.Smoke().values)
+    g.close()
+
+
 def test_apply_force_radius_and_misc_edits_match():
     from fluid_b200 import presets
     p = presets.jet(60, 40)
