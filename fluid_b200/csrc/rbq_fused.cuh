@@ -245,17 +245,9 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const unsigned c
 #define RQ_ROLES 18
 // Every lane arrives and every lane polls: measured faster than one arrive / one poller per
 // warp (lane-0 polling adds a divergent branch + __syncwarp to every hand-off: 0.35 -> 0.59 ms).
-#ifndef RQ_ARRIVE_MODE
-#define RQ_ARRIVE_MODE 0      // 0: every lane arrives (count = threads of the role); 1: one arrive per warp
-#endif
 __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line, int lane)
 {
-#if RQ_ARRIVE_MODE == 0
     rq_mbar_arrive(bars + role * RQ_RING + (line & (RQ_RING - 1)));
-#else
-    __syncwarp();
-    if (lane == 0) rq_mbar_arrive(bars + role * RQ_RING + (line & (RQ_RING - 1)));
-#endif
 }
 __device__ __forceinline__ void rq_wait_line(unsigned long long *bars, int role, int line)
 {
@@ -299,7 +291,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     if (tid == 0) rq_debug = P.debug;
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, ((role == 0 || role == 17) ? 128 : 32) / (RQ_ARRIVE_MODE ? 32 : 1));  // arrivals per phase
+        rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);  // arrivals per phase = threads of the role
     }
     if (tid < RQ_STG) rq_mbar_init(full + tid, 1);
     if (tid >= 32 && tid < 32 + RQ_WSTG) rq_mbar_init(wfull + tid - 32, 1);
@@ -358,68 +350,66 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const bool active = ld < (WL >> 2);
         const int j = jr0 + 4 * ld;
         const bool col_in = active && j >= 0 && j < PIT;
+        const bool v4_in = j + 4 < PIT;
         if (active) {   // the slot "below" line e0 (relative -1) must read as q = 0
             const int q = 2 * ld, b0 = (RQ_NL - 1) * ROW + q;
             *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
             *reinterpret_cast<float2 *>(sQ + b0 + WQ) = make_float2(0.f, 0.f);
         }
-        int sl = 0;
         const int last_owned = (i1c - 1) - e0;
+        // only interior lines inside this rank's slab hold updatable cells (the mask's count bits are
+        // zero on the ring and in solids); line e1 is loaded but never swept
+        const int live_lo = max(1, g.i_alloc0) - e0;
+        const int live_hi = min(min(NX - 2, g.i_alloc0 + g.lines_alloc - 2), e1 - 1) - e0;
+        const unsigned b_self = rq_s32(bars), b_writer = rq_s32(bars + 17 * RQ_RING), b_last = rq_s32(bars + nst * RQ_RING);
+        const unsigned b_full = rq_s32(full);
+        // element offset of this thread's cells in slot 0; staging offsets of lines rel and rel+1
+        int e_row = 2 * ld, sl = 0;
+        int st0 = 0, st1 = (RQ_STG > 1) ? 1 : 0;
+        unsigned par1 = 0;                                   // phase parity of staging slot st1's current use
+        rq_mbar_wait_a(b_full, 0u, (30 << 20));              // line 0 has landed
         for (int rel = 0; rel <= nproc; rel++) {
-            const int L = e0 + rel;
-            // only interior lines inside this rank's slab hold updatable cells; line e1 is never swept
-            const bool line_live = rel < nproc && L >= 1 && L <= NX - 2 && L >= g.i_alloc0 &&
-                                   L + 1 < g.i_alloc0 + g.lines_alloc;
             // slot(rel) last held line y-1 with y = rel-NL+1; its last readers work on line y: the writer
             // if y is an owned line, otherwise the last half sweep
-            {
-                const int y = rel - RQ_NL + 1;
-                if (y >= 0) {
-                    if (y >= RQ_H && y <= last_owned) rq_wait_line(bars, 17, y);
-                    else rq_wait_line(bars, nst, y);
-                }
+            const int y = rel - RQ_NL + 1;
+            if (y >= 0) {
+                const unsigned bb = (y >= RQ_H && y <= last_owned) ? b_writer : b_last;
+                rq_mbar_wait_a(bb + 8u * (unsigned)(y & (RQ_RING - 1)), (unsigned)(y >> 6) & 1u, (17 << 20) | y);
             }
             float d[4] = {0.f, 0.f, 0.f, 0.f};
             unsigned code = 0;
-            if (rel < nproc) {
-                // lines rel and rel+1 must have landed (the producer stages every line 0 .. nproc)
-                rq_wait_warp(full + (rel % RQ_STG), (rel / RQ_STG) & 1, (30 << 20) | rel);
-                rq_wait_warp(full + ((rel + 1) % RQ_STG), ((rel + 1) / RQ_STG) & 1, (31 << 20) | rel);
-            }
-            if (line_live && col_in) {
-                const unsigned char *s0 = stg + (rel % RQ_STG) * STG, *s1 = stg + ((rel + 1) % RQ_STG) * STG;
-                const float *stU = reinterpret_cast<const float *>(s0), *stV = stU + WL;
-                const float *stU1 = reinterpret_cast<const float *>(s1);
-                const unsigned char *stM = s0 + (size_t)(2 * WL + 4) * 4;
-                float u0[4], u1[4], v[5];
-                unpack(*reinterpret_cast<const float4 *>(stU + 4 * ld), u0);
-                unpack(*reinterpret_cast<const float4 *>(stU1 + 4 * ld), u1);
-                unpack(*reinterpret_cast<const float4 *>(stV + 4 * ld), v);
-                v[4] = (j + 4 < PIT) ? stV[4 * ld + 4] : 0.0f;
-                const unsigned mk = *reinterpret_cast<const unsigned *>(stM + 4 * ld);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const unsigned m = (mk >> (8 * k)) & 0xffu;
-                    const int jj = j + k;
-                    const unsigned ns = __popc(m & 30u);
-                    const bool upd = (m & MK_C) && ns > 0 && jj >= 1 && jj <= NY - 2;
-                    const float dv = ((u1[k] - u0[k]) + v[k + 1]) - v[k];
-                    d[k] = upd ? -dv : 0.0f;
-                    if (upd) code |= ns << (8 * k);
-                }
+            // line rel+1 must have landed too (the producer stages every line 0 .. nproc); line rel was
+            // waited for one iteration ago
+            if (rel < nproc) rq_mbar_wait_a(b_full + 8u * (unsigned)st1, par1, (31 << 20) | rel);
+            if (rel >= live_lo && rel <= live_hi && col_in) {
+                const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
+                const float *stU = reinterpret_cast<const float *>(s0) + 4 * ld, *stV = stU + WL;
+                const float4 u0 = *reinterpret_cast<const float4 *>(stU);
+                const float4 u1 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(s1) + 4 * ld);
+                const float4 v = *reinterpret_cast<const float4 *>(stV);
+                const float v4 = v4_in ? stV[4] : 0.0f;
+                const unsigned mk = *reinterpret_cast<const unsigned *>(s0 + (size_t)(2 * WL + 4) * 4 + 4 * ld);
+                code = (mk >> MK_CNT_SHIFT) & 0x07070707u;   // fluid neighbours of updatable cells, else 0
+                const float dv0 = ((u1.x - u0.x) + v.y) - v.x, dv1 = ((u1.y - u0.y) + v.z) - v.y;
+                const float dv2 = ((u1.z - u0.z) + v.w) - v.z, dv3 = ((u1.w - u0.w) + v4) - v.w;
+                d[0] = (code & 0x000000ffu) ? -dv0 : 0.0f;
+                d[1] = (code & 0x0000ff00u) ? -dv1 : 0.0f;
+                d[2] = (code & 0x00ff0000u) ? -dv2 : 0.0f;
+                d[3] = (code & 0xff000000u) ? -dv3 : 0.0f;
             }
             if (active) {
-                const int q = 2 * ld;
-                const int b0 = sl * ROW + q, b1 = b0 + WQ;
+                const int b0 = e_row, b1 = e_row + WQ;
                 *reinterpret_cast<float2 *>(sND + b0) = make_float2(d[0], d[2]);
                 *reinterpret_cast<float2 *>(sND + b1) = make_float2(d[1], d[3]);
                 *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
                 *reinterpret_cast<float2 *>(sQ + b1) = make_float2(0.f, 0.f);
-                *reinterpret_cast<unsigned short *>(sC + b0) = (unsigned short)((code & 0xffu) | ((code >> 8) & 0xff00u));
-                *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)(((code >> 8) & 0xffu) | ((code >> 16) & 0xff00u));
+                *reinterpret_cast<unsigned short *>(sC + b0) = (unsigned short)__byte_perm(code, 0u, 0x4420);
+                *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)__byte_perm(code, 0u, 0x4431);
             }
-            rq_done(bars, 0, rel, lane);                            // one arrive per loader warp
-            sl = sl + 1 == RQ_NL ? 0 : sl + 1;
+            rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));
+            if (++sl == RQ_NL) { sl = 0; e_row = 2 * ld; } else e_row += ROW;
+            st0 = st1;
+            if (++st1 == RQ_STG) { st1 = 0; par1 ^= 1u; }
         }
     } else if (warp < 24) {
         // ================= writer: owned lines -> U, V, p =================
@@ -430,59 +420,63 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const int st = tid - 640;
         const bool active = st < (P.TJ >> 2);
         const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
-        const bool col_ok = active && w_j < NY;
+        const bool col_ok = active && w_j < NY && !(P.xflags & 2);
+        const bool full4 = w_j + 3 < NY;
+        const unsigned b_self = rq_s32(bars + 17 * RQ_RING), b_last = rq_s32(bars + nst * RQ_RING), b_wfull = rq_s32(wfull);
         // only owned lines are written, but the hand-off phases count every line: arrive for the halo lines first
-        for (int rel = 0; rel < i0c - e0; rel++) rq_done(bars, 17, rel, lane);
+        for (int rel = 0; rel < i0c - e0; rel++) rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));
         int sl = (i0c - e0) % RQ_NL;
+        // this thread's cells: q index in a slot, staging offsets, global offset of line i0c
+        const int q = w_lj >> 1;
+        int e_row = sl * ROW + q, e_rowm = (sl == 0 ? RQ_NL - 1 : sl - 1) * ROW + q;
         int ws = 0;
         unsigned wpar = 0;
+        const unsigned char *sb = wstg + 16 * st;
+        const int oV = 4 * P.TJ, oM = 8 * P.TJ - 12 * st;    // byte offsets of V and the mask word from sb
+        size_t o = (size_t)(i0c - g.i_alloc0) * PIT + w_j;
+        const bool turb = P.turb > 0.0f;
+        const float cp = P.cp;
         for (int r = i0c; r < i1c; r++) {
             const int rel = r - e0;
-            rq_wait_line(bars, nst, rel);                     // last half sweep is past line r
-            rq_wait_warp(wfull + ws, wpar, (32 << 20) | rel); // U0, V0, mask of line r have landed
-            if (col_ok && !(P.xflags & 2)) {
-                const int o = (r - g.i_alloc0) * PIT + w_j;
-                const int slm = sl == 0 ? RQ_NL - 1 : sl - 1;
-                const int q = w_lj >> 1;
-                const unsigned char *sb = wstg + ws * WSTGB;
-                float u[4], v[4], pin[4] = {0.f, 0.f, 0.f, 0.f}, qc[4], qx[4], ql;
-                unpack(*reinterpret_cast<const float4 *>(sb + 16 * st), u);
-                unpack(*reinterpret_cast<const float4 *>(sb + 4 * P.TJ + 16 * st), v);
-                const unsigned m4 = *reinterpret_cast<const unsigned *>(sb + 8 * P.TJ + 4 * st);
+            rq_mbar_wait_a(b_last + 8u * (unsigned)(rel & (RQ_RING - 1)), (unsigned)(rel >> 6) & 1u, (nst << 20) | rel);   // last half sweep is past line r
+            rq_mbar_wait_a(b_wfull + 8u * (unsigned)ws, wpar, (32 << 20) | rel);     // U0, V0, mask of line r have landed
+            if (col_ok) {
+                const float4 u = *reinterpret_cast<const float4 *>(sb);
+                const float4 v = *reinterpret_cast<const float4 *>(sb + oV);
+                const unsigned m4 = *reinterpret_cast<const unsigned *>(sb + oM);
+                float pin[4] = {0.f, 0.f, 0.f, 0.f};
                 if (P.Pin) unpack(ld4(P.Pin + o), pin);
-                {
-                    const float2 ev = *reinterpret_cast<const float2 *>(sQ + sl * ROW + q);
-                    const float2 od = *reinterpret_cast<const float2 *>(sQ + sl * ROW + WQ + q);
-                    qc[0] = ev.x; qc[1] = od.x; qc[2] = ev.y; qc[3] = od.y;
-                    const float2 evm = *reinterpret_cast<const float2 *>(sQ + slm * ROW + q);
-                    const float2 odm = *reinterpret_cast<const float2 *>(sQ + slm * ROW + WQ + q);
-                    qx[0] = evm.x; qx[1] = odm.x; qx[2] = evm.y; qx[3] = odm.y;
-                    ql = sQ[sl * ROW + WQ + q - 1];                  // column lj-1 (odd parity, index q-1)
-                }
+                const float2 ev = *reinterpret_cast<const float2 *>(sQ + e_row);
+                const float2 od = *reinterpret_cast<const float2 *>(sQ + e_row + WQ);
+                const float2 evm = *reinterpret_cast<const float2 *>(sQ + e_rowm);
+                const float2 odm = *reinterpret_cast<const float2 *>(sQ + e_rowm + WQ);
+                const float ql = sQ[e_row + WQ - 1];                   // column lj-1 (odd parity, index q-1)
+                const float qc[4] = { ev.x, od.x, ev.y, od.y }, qx[4] = { evm.x, odm.x, evm.y, odm.y };
+                const float uu[4] = { u.x, u.y, u.z, u.w }, vv[4] = { v.x, v.y, v.z, v.w };
                 const bool line_first = (r == 0);
                 float pu[4], pv[4], pp[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const unsigned m = (m4 >> (8 * k)) & 0xffu;
+                    const unsigned m = m4 >> (8 * k);
                     const float qym = (k == 0) ? ql : qc[k - 1 < 0 ? 0 : k - 1];
                     const float a = (m & MK_XM) ? qc[k] : 0.0f;
                     const float b = ((m & MK_C) && !line_first) ? qx[k] : 0.0f;
-                    const float t1 = u[k] - a;
+                    const float t1 = uu[k] - a;
                     pu[k] = t1 + b;
                     const float a2 = (m & MK_YM) ? qc[k] : 0.0f;
                     const float b2 = ((m & MK_C) && (w_j + k) > 0) ? qym : 0.0f;
-                    const float t2 = v[k] - a2;
+                    const float t2 = vv[k] - a2;
                     pv[k] = t2 + b2;
-                    pp[k] = __fmaf_rn(P.cp, qc[k], pin[k]);
+                    pp[k] = __fmaf_rn(cp, qc[k], pin[k]);
                 }
-                if (P.turb > 0.0f && r >= 1 && r <= NX - 2) {        // fused addTurbulence (fluid.go:496-526)
+                if (turb && r >= 1 && r <= NX - 2) {                 // fused addTurbulence (fluid.go:496-526)
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const unsigned m = (m4 >> (8 * k)) & 0xffu;
+                        const unsigned m = m4 >> (8 * k);
                         const int jj = w_j + k;
                         if ((m & MK_C) && jj >= 1 && jj <= NY - 2) {
-                            const float uu = pu[k] * pu[k], vv = pv[k] * pv[k];
-                            const float localVel = sqrtf(uu + vv);
+                            const float u2 = pu[k] * pu[k], v2 = pv[k] * pv[k];
+                            const float localVel = sqrtf(u2 + v2);
                             if (localVel > 0.1f) {
                                 const float nu = __ldg(P.noiseU + o + k) * P.turb;
                                 const float nv = __ldg(P.noiseV + o + k) * P.turb;
@@ -494,13 +488,19 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                         }
                     }
                 }
-                store4(P.Uo + o, NY, w_j, pu);
-                store4(P.Vo + o, NY, w_j, pv);
-                store4(P.Po + o, NY, w_j, pp);
+                if (full4) {
+                    *reinterpret_cast<float4 *>(P.Uo + o) = make_float4(pu[0], pu[1], pu[2], pu[3]);
+                    *reinterpret_cast<float4 *>(P.Vo + o) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                    *reinterpret_cast<float4 *>(P.Po + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                } else {
+                    for (int k = 0; k < 4 && w_j + k < NY; k++) { P.Uo[o + k] = pu[k]; P.Vo[o + k] = pv[k]; P.Po[o + k] = pp[k]; }
+                }
             }
-            rq_done(bars, 17, rel, lane);                     // slots and staging of line r are free
-            sl = sl + 1 == RQ_NL ? 0 : sl + 1;
-            if (++ws == RQ_WSTG) { ws = 0; wpar ^= 1u; }
+            rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));       // slots and staging of line r are free
+            e_rowm = e_row;
+            if (++sl == RQ_NL) { sl = 0; e_row = q; } else e_row += ROW;
+            if (++ws == RQ_WSTG) { ws = 0; wpar ^= 1u; sb = wstg + 16 * st; } else sb += WSTGB;
+            o += PIT;
         }
     } else if (tid == 800) {
         // ================= second producer: U0, V0, mask of the owned lines for the writer =================
