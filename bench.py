@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--workload", default="karman4096", choices=sorted(WORKLOADS))
     ap.add_argument("--solver", default="pressure", choices=["pressure", "redblack", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo exchange between slabs (N > 1)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the exact-solver and e2e legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -231,12 +232,14 @@ def main():
         reach = parallel.reach_for(preset.dt, preset.h, 8.0)          # jets run at 4; allow 2x
         ghost = parallel.required_ghost(reach, bfecc, conf != 0.0)
         sim = parallel.SlabFluid(preset.density, preset.width, preset.height, preset.h, solver=solver, device=local,
-                                 rank=rank, nranks=world, ghost=ghost, reach=reach)
+                                 rank=rank, nranks=world, ghost=ghost, reach=reach, transport=args.transport)
         sim.edit(preset.init)
         sim.UseBFECC = bfecc
         sim.Confinement = conf
         cells_total = sim.global_cells
-        parallelism = f"row slabs over i, {world} ranks, {ghost} ghost lines, 1 NCCL halo exchange per step"
+        how = ("pulled from the neighbours' CUDA-IPC send buffers over NVLink (flag in peer memory, no collective)"
+               if args.transport == "peer" else "NCCL send/recv")
+        parallelism = f"row slabs over i, {world} ranks, {ghost} ghost lines, 1 halo exchange per step {how}"
     else:
         sim = make_fluid(fluid_b200, preset, solver, device=local)
         cells_total = sim.NumX * sim.NumY

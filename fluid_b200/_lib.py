@@ -68,6 +68,12 @@ SYMBOLS = {
     "fb_download": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "fb_host_mirror": (C.c_int, [_H, C.c_int32, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]),
     "fb_view": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fb_halo_export": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
+    "fb_halo_connect": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_uint64]),
+    "fb_halo_connect_local": (C.c_int, [_H, C.c_int32, _H]),
+    "fb_halo_post": (C.c_int, [_H]),
+    "fb_halo_pull": (C.c_int, [_H]),
+    "fb_halo_exchange": (C.c_int, [_H]),
     "fb_view_begin": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "fb_view_end": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fb_reduce": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_float)]),

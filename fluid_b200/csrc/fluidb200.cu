@@ -50,6 +50,15 @@ struct fb_handle {
     cudaStream_t copy_stream;     // device -> host leg of asynchronous views
     cudaEvent_t ev_snap, ev_view; // snapshot taken / view landed in host memory
     bool view_in_flight;
+    // peer-memory halo exchange (fb_halo_export / connect / exchange)
+    float *halo_send;             // [2 buffers][2 sides][3 fields][lines][pitch] + flags, IPC-exported
+    size_t halo_buf_floats;       // floats in one of the two buffers
+    int halo_lines;
+    unsigned halo_epoch;
+    const float *halo_peer[2];    // neighbours' send buffers (side 0 = lower i)
+    void *halo_peer_ipc[2];       // what cudaIpcOpenMemHandle returned (nullptr for same-process peers)
+    fb_handle *halo_peer_local[2];// same-process neighbours: their post is awaited with an event, not by spinning
+    cudaEvent_t ev_halo;          // recorded after every post
     bool prof;
     std::vector<cudaEvent_t> prof_pool;                 // recycled events
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pairs;
@@ -230,6 +239,9 @@ extern "C" int fb_destroy(fb_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int sd = 0; sd < 2; sd++) if (h->halo_peer_ipc[sd]) cudaIpcCloseMemHandle(h->halo_peer_ipc[sd]);
+    if (h->halo_send) cudaFree(h->halo_send);
+    if (h->ev_halo) cudaEventDestroy(h->ev_halo);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_view) cudaEventDestroy(h->ev_view);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -247,6 +259,131 @@ extern "C" int fb_dims(const fb_handle *h, int64_t *nx, int64_t *ny, int64_t *i_
     if (i_lo) *i_lo = h->g.i_lo;
     if (i_hi) *i_hi = h->g.i_hi;
     return FB_OK;
+}
+
+// ---- halo exchange through peer memory -----------------------------------------------------
+static inline size_t halo_total_bytes(const fb_handle *h) { return 2 * h->halo_buf_floats * sizeof(float) + 256; }
+static inline unsigned *halo_flags(const fb_handle *h, const float *base, int buf)
+{
+    return reinterpret_cast<unsigned *>(const_cast<float *>(base) + 2 * h->halo_buf_floats) + 16 * buf;
+}
+
+extern "C" int fb_halo_export(fb_handle *h, int32_t lines, void *ipc_handle64, uint64_t *device_ptr, size_t *bytes)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    if (lines < 1 || lines > h->cfg.ghost) return fail(h, FB_ERR_INVALID, "halo wider than the ghost zone");
+    if (lines > g.i_hi - g.i_lo) return fail(h, FB_ERR_INVALID, "halo wider than the slab");
+    if (h->halo_send && h->halo_lines != lines) return fail(h, FB_ERR_INVALID, "halo width cannot change after export");
+    if (!h->halo_send) {
+        h->halo_lines = lines;
+        h->halo_buf_floats = (size_t)6 * lines * g.pitch;
+        CK(cudaMalloc(&h->halo_send, halo_total_bytes(h)));
+        CK(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+        CK(cudaMemsetAsync(h->halo_send, 0, halo_total_bytes(h), h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t mh;
+        static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        CK(cudaIpcGetMemHandle(&mh, h->halo_send));
+        memcpy(ipc_handle64, &mh, 64);
+    }
+    if (device_ptr) *device_ptr = (uint64_t)(uintptr_t)h->halo_send;
+    if (bytes) *bytes = halo_total_bytes(h);
+    return FB_OK;
+}
+
+extern "C" int fb_halo_connect(fb_handle *h, int32_t side, const void *ipc_handle64, uint64_t device_ptr)
+{
+    if (!h || side < 0 || side > 1) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->halo_send) return fail(h, FB_ERR_INVALID, "fb_halo_connect before fb_halo_export");
+    const Grid &g = h->g;
+    const int recv_i = side == 0 ? g.i_lo - h->halo_lines : g.i_hi;
+    if (recv_i < g.i_alloc0 || recv_i + h->halo_lines > g.i_alloc0 + g.lines_alloc)
+        return fail(h, FB_ERR_INVALID, "no neighbour on that side");
+    if (h->halo_peer_ipc[side]) { cudaIpcCloseMemHandle(h->halo_peer_ipc[side]); h->halo_peer_ipc[side] = nullptr; }
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, ipc_handle64, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->halo_peer_ipc[side] = p;
+        h->halo_peer[side] = static_cast<const float *>(p);
+    } else {
+        if (!device_ptr) return fail(h, FB_ERR_INVALID, "fb_halo_connect: neither an IPC handle nor a device pointer");
+        h->halo_peer[side] = reinterpret_cast<const float *>((uintptr_t)device_ptr);   // same process
+    }
+    return FB_OK;
+}
+
+// Same-process neighbour (several handles in one process, possibly on one device): attach by handle.
+// Its post is then awaited with a stream-ordered event before the pull is launched, so that the
+// pull kernel never spins on a device that still has to run the post it waits for.
+extern "C" int fb_halo_connect_local(fb_handle *h, int32_t side, fb_handle *peer)
+{
+    if (!h || !peer || side < 0 || side > 1) return FB_ERR_INVALID;
+    if (!peer->halo_send) return fail(h, FB_ERR_INVALID, "fb_halo_connect_local: the peer has not exported");
+    TRY(fb_halo_connect(h, side, nullptr, (uint64_t)(uintptr_t)peer->halo_send));
+    h->halo_peer_local[side] = peer;
+    return FB_OK;
+}
+
+// phase 1 of an exchange: pack the boundary lines and publish the epoch (never waits)
+extern "C" int fb_halo_post(fb_handle *h)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->halo_send) return fail(h, FB_ERR_INVALID, "fb_halo_post before fb_halo_export");
+    const Grid &g = h->g;
+    h->halo_epoch++;
+    const int buf = (int)(h->halo_epoch & 1u);
+    HaloPack a;
+    a.src[0] = h->f[FB_U]; a.src[1] = h->f[FB_V]; a.src[2] = h->f[FB_M];
+    a.dst = h->halo_send + (size_t)buf * h->halo_buf_floats;
+    a.i_lo = g.i_lo; a.i_hi = g.i_hi; a.lines = h->halo_lines; a.pitch = g.pitch; a.i_alloc0 = g.i_alloc0;
+    k_halo_pack<<<dim3(cdiv(g.pitch / 4, 256), h->halo_lines, 6), 256, 0, h->stream>>>(a);
+    CKL("k_halo_pack");
+    k_halo_publish<<<1, 1, 0, h->stream>>>(halo_flags(h, h->halo_send, buf), h->halo_epoch);
+    CKL("k_halo_publish");
+    CK(cudaEventRecord(h->ev_halo, h->stream));
+    return FB_OK;
+}
+
+// phase 2: pull the ghost lines out of the connected neighbours' send buffers (waits on their flags)
+extern "C" int fb_halo_pull(fb_handle *h)
+{
+    if (!h) return FB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->halo_send) return fail(h, FB_ERR_INVALID, "fb_halo_pull before fb_halo_export");
+    if (!h->halo_peer[0] && !h->halo_peer[1]) return FB_OK;
+    const Grid &g = h->g;
+    const int buf = (int)(h->halo_epoch & 1u);
+    HaloPull a;
+    a.dst[0] = h->f[FB_U]; a.dst[1] = h->f[FB_V]; a.dst[2] = h->f[FB_M];
+    for (int sd = 0; sd < 2; sd++) {
+        a.peer[sd] = h->halo_peer[sd] ? h->halo_peer[sd] + (size_t)buf * h->halo_buf_floats : nullptr;
+        a.peer_flag[sd] = h->halo_peer[sd] ? halo_flags(h, h->halo_peer[sd], buf) : nullptr;
+    }
+    a.recv_i[0] = g.i_lo - h->halo_lines; a.recv_i[1] = g.i_hi;
+    a.lines = h->halo_lines; a.pitch = g.pitch; a.i_alloc0 = g.i_alloc0; a.epoch = h->halo_epoch; a.bad = h->d_bad;
+    for (int sd = 0; sd < 2; sd++)
+        if (h->halo_peer_local[sd]) {
+            if (h->halo_peer_local[sd]->halo_epoch != h->halo_epoch)
+                return fail(h, FB_ERR_INVALID, "fb_halo_pull: a same-process neighbour has not posted this exchange yet");
+            CK(cudaStreamWaitEvent(h->stream, h->halo_peer_local[sd]->ev_halo, 0));
+        }
+    k_halo_pull<<<dim3(cdiv(g.pitch / 4, 256), h->halo_lines, 6), 256, 0, h->stream>>>(a);
+    CKL("k_halo_pull");
+    return FB_OK;
+}
+
+extern "C" int fb_halo_exchange(fb_handle *h)
+{
+    TRY(fb_halo_post(h));
+    return fb_halo_pull(h);
 }
 
 extern "C" int fb_ghost_lines(const fb_handle *h, int32_t *ghost)
@@ -372,6 +509,7 @@ static int check_bad(fb_handle *h)
     CK(cudaStreamSynchronize(h->stream));
     if (bad) {
         CK(cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+        if (bad == 2) return fail(h, FB_ERR_HALO, "halo exchange: a neighbour never published its boundary lines");
         return fail(h, FB_ERR_HALO, "semi-Lagrangian trace left the ghost zone; create the handle with more ghost lines");
     }
     return FB_OK;

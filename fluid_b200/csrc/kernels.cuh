@@ -789,3 +789,54 @@ __global__ void k_edit_one(Grid g, EditFields f, fb_edit_cmd c)
     if (j >= j0 + nj) return;
     for (int i = i0 + blockIdx.y; i < i0 + ni; i += gridDim.y) apply_edit_cell(g, f, c, i, j);
 }
+
+// ---- halo exchange through peer memory (NVLink P2P) --------------------------------------
+// Every rank PACKS the `lines` owned lines next to each slab boundary of U, V, M into a send
+// buffer of its own (exported to the neighbours by CUDA IPC), PUBLISHES the exchange epoch in a
+// flag next to it, and PULLS its ghost lines straight out of the neighbours' send buffers.  The
+// pull waits on the neighbour's flag, so there is no host hand-shake and no collective; two
+// buffers alternate so that a rank may pack epoch k+2 only after its own pull of k+1, which the
+// neighbour's pack of k+1 (after ITS pull of k) precedes.
+struct HaloPack { const float *src[3]; float *dst; int i_lo, i_hi, lines, pitch, i_alloc0; };
+__global__ void k_halo_pack(HaloPack a)
+{
+    // grid: (pitch/4 / 256, lines, 6): z = side * 3 + field
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y, side = blockIdx.z / 3, field = blockIdx.z % 3;
+    if (4 * c4 >= a.pitch) return;
+    const int i = side == 0 ? a.i_lo + l : a.i_hi - a.lines + l;
+    const float4 v = *reinterpret_cast<const float4 *>(a.src[field] + (size_t)(i - a.i_alloc0) * a.pitch + 4 * c4);
+    *reinterpret_cast<float4 *>(a.dst + ((size_t)(side * 3 + field) * a.lines + l) * a.pitch + 4 * c4) = v;
+}
+__global__ void k_halo_publish(unsigned *flags, unsigned epoch)
+{
+    __threadfence_system();
+    reinterpret_cast<volatile unsigned *>(flags)[0] = epoch;
+    __threadfence_system();
+}
+struct HaloPull { float *dst[3]; const float *peer[2]; const unsigned *peer_flag[2]; int recv_i[2]; int lines, pitch, i_alloc0; unsigned epoch; int *bad; };
+__global__ void k_halo_pull(HaloPull a)
+{
+    // grid: (pitch/4 / 256, lines, 6): z = side * 3 + field; side s reads the neighbour's region 1 - s
+    const int side = blockIdx.z / 3, field = blockIdx.z % 3;
+    if (!a.peer[side]) return;
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        const volatile unsigned *f = a.peer_flag[side];
+        int good = 0;
+        for (unsigned spin = 0; spin < (1u << 26); spin++) {
+            if ((int)(*f - a.epoch) >= 0) { good = 1; break; }
+            __nanosleep(200);
+        }
+        if (!good) atomicExch(a.bad, 2);          // the neighbour never published: FB_ERR_HALO at the next check
+        __threadfence_system();
+        ok = good;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (4 * c4 >= a.pitch) return;
+    const float4 v = __ldcv(reinterpret_cast<const float4 *>(a.peer[side] + ((size_t)((1 - side) * 3 + field) * a.lines + l) * a.pitch + 4 * c4));
+    *reinterpret_cast<float4 *>(a.dst[field] + (size_t)(a.recv_i[side] + l - a.i_alloc0) * a.pitch + 4 * c4) = v;
+}

@@ -7,8 +7,12 @@ Rank r owns interior lines ``1 + W*r/R .. 1 + W*(r+1)/R`` (the ring lines 0 and
 NumX-1 go to the first / last rank) plus ``ghost`` lines on each side.
 
 Per step there is ONE exchange: the ``ghost`` lines of U, V and M on each side
-are refreshed from the neighbours (NCCL send/recv over NVLink, queued on the
-library's own CUDA stream, nothing blocks the host).  Inside the step every
+are refreshed from the neighbours.  Default transport ``"peer"``: every rank packs
+its boundary lines into a send buffer exported with CUDA IPC and pulls its ghost
+lines straight out of the neighbours' buffers over NVLink, the pull kernel waiting
+on an epoch flag in peer memory (fb_halo_exchange) -- no collective, no host
+hand-shake, three kernels on the library's own stream.  Transport ``"nccl"``:
+send/recv of the same lines through torch.distributed (kept for comparison).  Inside the step every
 phase is recomputed redundantly on as many ghost lines as later phases read
 (``fb_step_local``), so results are bit-identical to the single-GPU run.  Views and
 reductions are local passes followed by a max/min all-reduce of two floats.
@@ -85,9 +89,16 @@ def exchange_halos(dist, regions, plan, group=None):
 
 def exchange_local(slabs):
     """Halo exchange between slabs that live in ONE process (several handles on one or
-    more devices): plain device-to-device copies on the slabs' streams.  Used by the
-    single-GPU slab-equivalence tests; the multi-process path uses exchange_halos."""
+    more devices).  Peer transport: the same pack / publish / pull kernels as between
+    processes, connected by device address; every slab posts before any slab pulls.
+    Otherwise plain device-to-device copies."""
     import torch
+    if slabs and slabs[0].transport == "peer":
+        for s in slabs:
+            L.check(s.f._h, L.lib.fb_halo_post(s.f._h))
+        for s in slabs:
+            L.check(s.f._h, L.lib.fb_halo_pull(s.f._h))
+        return
     for s in slabs:
         s.f.synchronize()
     regs = [s._regions() for s in slabs]
@@ -116,7 +127,7 @@ class SlabFluid:
     EXCHANGED = (L.U, L.V, L.M)
 
     def __init__(self, density, width, height, h, *, solver=L.SOLVER_REDBLACK_PRESSURE, device=0, rank=0,
-                 nranks=1, ghost=48, reach=6):
+                 nranks=1, ghost=48, reach=6, transport="peer", connect=True):
         import torch
         import torch.distributed as dist
         if solver == L.SOLVER_EXACT:
@@ -134,6 +145,29 @@ class SlabFluid:
         self.stream = torch.cuda.ExternalStream(self.f.cuda_stream(), device=torch.device("cuda", device)) \
             if nranks > 1 else None
         self._steps_since_check = 0
+        if transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
+        self.transport = transport if nranks > 1 else "none"
+        if self.transport == "peer" and connect:
+            self.connect_peers()
+
+    # ---- peer-memory transport ---------------------------------------------------------------
+    def export_halo(self):
+        """(ipc_handle_bytes, device_address) of this rank's send buffer."""
+        handle = (C.c_ubyte * 64)()
+        ptr, nbytes = C.c_uint64(), C.c_size_t()
+        L.check(self.f._h, L.lib.fb_halo_export(self.f._h, self.ghost, handle, C.byref(ptr), C.byref(nbytes)))
+        return bytes(handle), int(ptr.value)
+
+    def connect_peers(self):
+        """One process per GPU: all-gather the IPC handles and attach both neighbours."""
+        handle, _ptr = self.export_halo()
+        gathered = [None] * self.nranks
+        self.dist.all_gather_object(gathered, handle)
+        for side, peer in self.plan:
+            buf = (C.c_ubyte * 64).from_buffer_copy(gathered[peer])
+            L.check(self.f._h, L.lib.fb_halo_connect(self.f._h, side, buf, 0))
+        self.dist.barrier()
 
     # knobs are forwarded to the slab's Fluid
     def __getattr__(self, name):
@@ -170,6 +204,9 @@ class SlabFluid:
 
     def exchange(self):
         if self.nranks == 1:
+            return
+        if self.transport == "peer":
+            L.check(self.f._h, L.lib.fb_halo_exchange(self.f._h))
             return
         with self.torch.cuda.stream(self.stream):
             exchange_halos(self.dist, self._regions(), self.plan)
@@ -252,10 +289,16 @@ class LocalSlabGroup:
     used to check slab-vs-single-domain bit identity on a single-GPU box."""
 
     def __init__(self, density, width, height, h, nslabs, *, solver=L.SOLVER_REDBLACK_PRESSURE, devices=None,
-                 ghost=48, reach=6):
+                 ghost=48, reach=6, transport="peer"):
         devices = devices or [0] * nslabs
         self.slabs = [SlabFluid(density, width, height, h, solver=solver, device=devices[r], rank=r, nranks=nslabs,
-                                ghost=ghost, reach=reach) for r in range(nslabs)]
+                                ghost=ghost, reach=reach, transport=transport, connect=False) for r in range(nslabs)]
+        if transport == "peer" and nslabs > 1:
+            for s in self.slabs:
+                s.export_halo()
+            for s in self.slabs:                                    # same process: attach by handle
+                for side, peer in s.plan:
+                    L.check(s.f._h, L.lib.fb_halo_connect_local(s.f._h, side, self.slabs[peer].f._h))
         self.NumX, self.NumY = self.slabs[0].NumX, self.slabs[0].NumY
 
     def __setattr__(self, name, value):

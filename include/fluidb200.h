@@ -212,6 +212,24 @@ int fb_sample_velocity(fb_handle *h, size_t n, const float *xy, float *uv);
 int fb_halo_region(fb_handle *h, int32_t field, int32_t side, int32_t lines,
                    void **send_ptr, void **recv_ptr, size_t *bytes);
 int fb_ghost_lines(const fb_handle *h, int32_t *ghost);
+/* Halo exchange through peer memory (NVLink P2P), no collective and no host hand-shake.
+ *   fb_halo_export   allocate this rank's send buffer for `lines` lines per side of U, V, M and
+ *                    return its CUDA IPC handle (64 bytes) and its device address;
+ *   fb_halo_connect  attach the send buffer of the neighbour on `side` (0 = lower i): by IPC
+ *                    handle (another process on the node) or by device address (same process);
+ *   fb_halo_post     pack the boundary lines and publish the exchange epoch (never waits);
+ *   fb_halo_pull     copy the ghost lines out of the neighbours' buffers; the kernel waits on
+ *                    their epoch flags (bounded: a neighbour that never posts -> FB_ERR_HALO);
+ *   fb_halo_exchange post + pull.  Every rank calls it once before each fb_step_local.
+ * All work is queued on the handle's stream.  Handles of ONE process must post all before any
+ * pulls (the pull would otherwise spin in front of the post it waits for). */
+int fb_halo_export(fb_handle *h, int32_t lines, void *ipc_handle64, uint64_t *device_ptr, size_t *bytes);
+int fb_halo_connect(fb_handle *h, int32_t side, const void *ipc_handle64_or_null, uint64_t device_ptr);
+/* neighbour handle of the same process: its post is awaited with an event instead of a spinning pull */
+int fb_halo_connect_local(fb_handle *h, int32_t side, fb_handle *peer);
+int fb_halo_post(fb_handle *h);
+int fb_halo_pull(fb_handle *h);
+int fb_halo_exchange(fb_handle *h);
 /* FB_ERR_HALO if any trace since the last check read outside the lines this rank holds
  * (synchronises the stream; call it every few steps, not every step). */
 int fb_check_halo(fb_handle *h);

@@ -28,12 +28,13 @@ def main():
     failures = 0
     cases = [presets.jet(256 * world, 192), presets.karman(200 * world, 160),
              presets.karman(240 * world, 128, bfecc=False, confinement=0.0)]
-    for p in cases:
+    transports = ["peer", "peer", "nccl"]      # halo exchange: CUDA-IPC peer memory (default) and NCCL send/recv
+    for p, transport in zip(cases, transports):
         bfecc = bool(p.params.get("use_bfecc", False))
         conf = float(p.params.get("confinement", 0.0))
         reach = 6
         slab = SlabFluid(p.density, p.width, p.height, p.h, solver=2, device=local, rank=rank, nranks=world,
-                         ghost=required_ghost(reach, bfecc, conf != 0.0), reach=reach)
+                         ghost=required_ghost(reach, bfecc, conf != 0.0), reach=reach, transport=transport)
         slab.edit(p.init)
         slab.UseBFECC = bfecc
         slab.Confinement = conf
@@ -50,7 +51,7 @@ def main():
             for name, got in fields.items():
                 want = single.get(name)
                 bad = int(np.count_nonzero(~((got == want) | (np.isnan(got) & np.isnan(want)))))
-                print(f"[{p.name} {p.width}x{p.height} bfecc={bfecc} conf={conf}] {name}: mismatches={bad}")
+                print(f"[{p.name} {p.width}x{p.height} bfecc={bfecc} conf={conf} {transport}] {name}: mismatches={bad}")
                 failures += bad != 0
             assert np.float32(md) == np.float32(single.MaxDivergence())
             single.close()
