@@ -438,12 +438,15 @@ def test_parity_report_three_presets():
     print("\nPARITY_REPORT " + repr(rows))
 
 
-@pytest.mark.parametrize("preset_name,nslabs", [("jet", 2), ("karman", 2), ("cavity", 3), ("karman_plain", 4)])
-def test_slab_decomposition_is_bit_identical(preset_name, nslabs):
+@pytest.mark.parametrize("preset_name,nslabs,transport", [("jet", 2, "peer"), ("karman", 2, "peer"), ("cavity", 3, "peer"),
+                                                          ("karman_plain", 4, "peer"), ("karman", 3, "nccl")])
+def test_slab_decomposition_is_bit_identical(preset_name, nslabs, transport):
     """Row slabs with ghost lines, one halo exchange per step and redundant ghost
     computation (fb_step_local) give exactly the single-domain result.  The slabs live in
-    one process here (exchange by device copies); the multi-process NCCL path runs the same
-    fb_step_local / fb_halo_region calls (tests/multi_gpu_check.py)."""
+    one process here: transport "peer" runs the library's own pack / publish / pull kernels
+    (fb_halo_post / fb_halo_pull, neighbours attached by handle), "nccl" stands in for the
+    send/recv path with plain device copies of the fb_halo_region lines.  The multi-process
+    versions of both run in tests/multi_gpu_check.py."""
     import fluid_b200
     from fluid_b200 import presets
     from fluid_b200.parallel import LocalSlabGroup, required_ghost
@@ -454,7 +457,8 @@ def test_slab_decomposition_is_bit_identical(preset_name, nslabs):
     reach = 6
     ghost = required_ghost(reach, bfecc, conf)
     single = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
-    group = LocalSlabGroup(p.density, p.width, p.height, p.h, nslabs, solver=2, ghost=ghost, reach=reach)
+    group = LocalSlabGroup(p.density, p.width, p.height, p.h, nslabs, solver=2, ghost=ghost, reach=reach,
+                           transport=transport)
     for f in (single, group):
         f.edit(p.init)
         f.UseBFECC = bfecc
