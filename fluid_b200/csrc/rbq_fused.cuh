@@ -14,23 +14,39 @@
 // checked bit for bit against its own CPU restatement fo_project_redblack_q.
 //
 // Structure: a CTA owns `chunk` lines x TJ columns (+16-cell halo, recomputed).  Lines
-// (constant i, contiguous in j) stream through a ring of 35 slots in 220 KB of shared
-// memory.  24 warps form a software pipeline WITHOUT block-wide barriers:
-//   thread 768   producer TMA bulk copies (cp.async.bulk + mbarrier) of the U, V, mask segments
-//                         of a line into a 4-deep staging ring, 4 lines ahead of the loader
-//   warps 16-19  loader   staging -> -D0, 1/s, q=0 in slot(L)
+// (constant i, contiguous in j) stream through a ring of 35 slots in 223 KB of shared
+// memory.  26 warps form a software pipeline WITHOUT block-wide barriers:
+//   thread 768   producer 1: TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the U, V,
+//                mask segments of a line into a 4-deep staging ring, 4 lines ahead of the loader
+//   warps 16-19  loader: staging -> -D0, neighbour count (bits 5-7 of the mask byte), q = 0 in slot(L)
 //   warp  s<16   half sweep s (colour s&1): may process line r once its predecessor
 //                (loader for s=0, warp s-1 otherwise) has finished line r+1
-//   warps 20-23  writer   slot(r), slot(r-1) + U0,V0 -> U,V,p in global     (register prefetch, 3 lines)
-// Each role publishes the last line it finished with st.release.cta and waits on its
-// predecessor with ld.acquire.cta; the loader reuses a slot once the writer is past it.
+//   thread 800   producer 2: TMA bulk copies of U0, V0, mask of the OWNED columns of the owned
+//                lines into an 8-deep ring for the writer
+//   warps 20-23  writer: slot(r), slot(r-1) + U0, V0, mask from its ring -> U, V, p in global
+// Hand-offs are per-line mbarriers (64 per role; every lane of the role arrives, every lane of
+// the successor polls with try_wait); the loader reuses a slot once the writer (or, for halo
+// lines, the last half sweep) is past it.  Waits are bounded: a pipeline that stops latches a
+// debug record and the host returns FB_ERR_CUDA instead of hanging the GPU.
 // Even and odd columns live in separate arrays so one colour is contiguous: a lane
 // updates 2 x 4 consecutive same-colour cells with LDS.128 / STS.128 and packed
 // FADD2 / FFMA2 (sm_100a fp32x2, bit-identical to the scalar operations).
 //
-// Why this shape: ncu showed the face form (rb_fused.cuh) issue-bound at ~110
-// instructions per cell update and the first pressure-form version stalled on its
-// per-line __syncthreads (barrier = 3.4 of 9 stall cycles per issue).
+// Why this shape (ncu, 4098^2, 8 iterations; time of the solve):
+//   face form (rb_fused.cuh), ~110 instructions per cell update, issue-bound          1.11 ms
+//   pressure form, one __syncthreads per line (barrier = 3.4 of 9 stall cycles)       0.47
+//   warp-specialised roles with mbarrier hand-offs, strips x chunks = one wave        0.31
+//   writer inputs through TMA: its re-read of U0, V0 missed L2 two times in three and
+//   the register prefetch ring did not survive code generation (74 % of the writer's
+//   stall samples sat on the first use of those loads)                                0.226
+//   neighbour counts baked into the mask, lean loader / writer loops                  0.211
+// Now issue slots are 73 % and shared-memory wavefronts 74 % busy, DRAM 25 %.  Measured and NOT
+// adopted: one arrive per warp instead of 32 (no change); a 2-instruction poll loop (0.224:
+// try_wait is a shared-memory operation, faster polling takes wavefronts from the sweeps);
+// nanosleep after a failed poll (no change); 37 / 40 ring slots, 8-deep loader staging (no
+// change); re-reading the neighbour vectors instead of carrying them (0.231: LSU pipe 79 %);
+// turbulence fused into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2); four
+// lines in flight per loader / writer warp (0.47).
 #pragma once
 #include "kernels.cuh"
 #include "advect_fused.cuh"
@@ -45,8 +61,9 @@
 #ifndef RQ_STG
 #define RQ_STG 4          // staging ring depth (lines in flight through TMA)
 #endif
-// shared memory: 35 slots * WL * 9 B (q, -D0, neighbour count) + RQ_STG * (WL*9 + 16) B staging
-//                + hand-off mbarriers = 146.2 KB + 16.4 KB + 9.2 KB at WL = 464
+// shared memory at WL = 512, TJ = 464: 35 slots * WL * 9 B (q, -D0, neighbour count) = 157.5 KB, loader
+// staging RQ_STG * (WL*9 + 16) B = 18.1 KB, writer staging RQ_WSTG * TJ * 9 B = 32.6 KB, hand-off
+// mbarriers 9.1 KB, wd/s table 0.5 KB: 217.8 KB of the 227 KB a CTA may have
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
 #ifndef RQ_WSTG
 #define RQ_WSTG 8         // writer staging ring depth
