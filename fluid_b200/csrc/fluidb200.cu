@@ -827,6 +827,7 @@ static AdvCtx adv_ctx(const fb_handle *h)
     const Grid &g = h->g;
     AdvCtx c;
     c.NX = g.NX; c.NY = g.NY; c.pitch = g.pitch; c.i_alloc0 = g.i_alloc0; c.lines_alloc = g.lines_alloc;
+    c.xr_hi = (g.i_alloc0 + g.lines_alloc == g.NX) ? g.lines_alloc - 1 : g.lines_alloc - 2;
     volatile float hh = h->cfg.h;
     volatile float h1 = 1.0f / hh, h2 = hh / 2.0f;
     volatile float xmax = (float)g.NX * hh, ymax = (float)g.NY * hh;
