@@ -8,4 +8,4 @@ there is no CPU path.
 """
 from . import edits, presets  # noqa: F401
 from ._lib import FluidError, SOLVER_EXACT, SOLVER_REDBLACK, SOLVER_REDBLACK_PRESSURE  # noqa: F401
-from .fluid import Fluid, New, ScalarField, VectorField  # noqa: F401
+from .fluid import Fluid, New, PARTICLE_DTYPE, ScalarField, VectorField  # noqa: F401

@@ -76,6 +76,10 @@ SYMBOLS = {
     "fb_halo_exchange": (C.c_int, [_H]),
     "fb_view_begin": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "fb_view_end": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fb_render_begin": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]),
+    "fb_render_end": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fb_render": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fb_advect_particles": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_float, C.POINTER(C.c_size_t)]),
     "fb_reduce": (C.c_int, [_H, C.c_int32, C.POINTER(C.c_float)]),
     "fb_sample_velocity": (C.c_int, [_H, C.c_size_t, C.c_void_p, C.c_void_p]),
     "fb_halo_region": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

@@ -57,6 +57,8 @@ struct fb_handle {
     unsigned halo_epoch;
     const float *halo_peer[2];    // neighbours' send buffers (side 0 = lower i)
     void *halo_peer_ipc[2];       // what cudaIpcOpenMemHandle returned (nullptr for same-process peers)
+    fb_particle_dev *d_particles; int *d_alive; size_t particles_cap;   // fb_advect_particles scratch
+    std::vector<int> h_alive;
     fb_handle *halo_peer_local[2];// same-process neighbours: their post is awaited with an event, not by spinning
     cudaEvent_t ev_halo;          // recorded after every post
     bool prof;
@@ -241,6 +243,8 @@ extern "C" int fb_destroy(fb_handle *h)
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int sd = 0; sd < 2; sd++) if (h->halo_peer_ipc[sd]) cudaIpcCloseMemHandle(h->halo_peer_ipc[sd]);
     if (h->halo_send) cudaFree(h->halo_send);
+    if (h->d_particles) cudaFree(h->d_particles);
+    if (h->d_alive) cudaFree(h->d_alive);
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_view) cudaEventDestroy(h->ev_view);
@@ -1556,6 +1560,113 @@ extern "C" int fb_view_end(fb_handle *h, float *min_value, float *max_value)
     h->view_in_flight = false;
     if (min_value) *min_value = key2f(h->h_red[32]);
     if (max_value) *max_value = key2f(h->h_red[33]);
+    return FB_OK;
+}
+
+// ---- Draw's pixel pass and advectParticles on the device -----------------
+// fb_render_begin / fb_render_end: like fb_view_begin / fb_view_end, but what travels is the RGBA image
+// main/main.go:550-574 builds from the view (colormap of main/colors.go, solid cells black), in the
+// image layout of fluidToImageIndex (main.go:795): [NumY rows][NumX pixels][4 bytes], row jj showing
+// fluid column NumY-1-jj.  `range` = {min, max} to colour with (a multi-GPU host passes the
+// all-reduced pair); NULL = this handle's own min / max of the view (Q-14 semantics).
+extern "C" int fb_render_begin(fb_handle *h, int32_t kind, uint8_t *rgba_out, const float *color_range)
+{
+    if (!h || !rgba_out) return FB_ERR_INVALID;
+    if (h->view_in_flight) return fail(h, FB_ERR_INVALID, "fb_render_begin: a view is already in flight");
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_view, cudaEventDisableTiming));
+    }
+    float *snap;
+    TRY(scratch(h, SCR_SNAP, &snap));          // the image: (ie - ib) * NumY pixels of 4 bytes, a plane holds them
+    k_minmax_init<<<1, 1, 0, h->stream>>>(h->d_red + 32);
+    CKL("k_minmax_init");
+    const float *src = nullptr;
+    switch (kind) {
+    case FB_VIEW_SMOKE: src = h->f[FB_M]; break;
+    case FB_VIEW_PRESSURE: src = h->f[FB_P]; break;
+    case FB_VIEW_VELOCITY_MAGNITUDE: case FB_VIEW_VORTICITY: {
+        float *view;
+        TRY(scratch(h, SCR_VIEW, &view));
+        if (kind == FB_VIEW_VORTICITY)
+            k_view<FB_VIEW_VORTICITY><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        else
+            k_view<FB_VIEW_VELOCITY_MAGNITUDE><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        CKL("k_view");
+        src = view;
+        break;
+    }
+    default: return fail(h, FB_ERR_INVALID, "unknown view");
+    }
+    if (kind == FB_VIEW_SMOKE || kind == FB_VIEW_PRESSURE) {
+        k_minmax_all<<<grid, block, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
+        CKL("k_minmax_all");
+    }
+    if (color_range) {
+        k_minmax_set<<<1, 1, 0, h->stream>>>(h->d_red + 32, color_range[0], color_range[1]);
+        CKL("k_minmax_set");
+    }
+    const dim3 rgrid(cdiv(g.NY, 32), cdiv(ie - ib, 32), 1), rblock(32, 8, 1);
+    unsigned *img = reinterpret_cast<unsigned *>(snap);
+    if (kind == FB_VIEW_VORTICITY) k_render<1><<<rgrid, rblock, 0, h->stream>>>(g, src, h->f[FB_S], h->d_red + 32, img, ib, ie);
+    else k_render<0><<<rgrid, rblock, 0, h->stream>>>(g, src, h->f[FB_S], h->d_red + 32, img, ib, ie);
+    CKL("k_render");
+    CK(cudaEventRecord(h->ev_snap, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    // this rank's pixel columns [ib, ie) of every image row
+    CK(cudaMemcpy2DAsync(rgba_out + (size_t)ib * 4, (size_t)g.NX * 4, img, (size_t)(ie - ib) * 4, (size_t)(ie - ib) * 4,
+                         (size_t)g.NY, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(h->ev_view, h->copy_stream));
+    h->view_in_flight = true;
+    return FB_OK;
+}
+
+extern "C" int fb_render_end(fb_handle *h, float *min_value, float *max_value) { return fb_view_end(h, min_value, max_value); }
+
+extern "C" int fb_render(fb_handle *h, int32_t kind, uint8_t *rgba_out, const float *color_range, float *min_value, float *max_value)
+{
+    TRY(fb_render_begin(h, kind, rgba_out, color_range));
+    return fb_render_end(h, min_value, max_value);
+}
+
+// advectParticles (main/main.go:512-546) for n particles in host memory, in place; survivors keep their
+// order (the reference's `alive = append(alive, *p)`), *n_alive says how many.  The four bilinear samples
+// per particle run on the device; the stable filter is a host pass over the flags that came back.
+extern "C" int fb_advect_particles(fb_handle *h, fb_particle *particles, size_t n, float dt, size_t *n_alive)
+{
+    if (!h || (n && !particles) || !n_alive) return FB_ERR_INVALID;
+    static_assert(sizeof(fb_particle) == sizeof(fb_particle_dev), "particle layouts must match");
+    *n_alive = 0;
+    if (n == 0) return FB_OK;
+    CK(cudaSetDevice(h->device));
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "fb_advect_particles: particles roam the whole grid; single-GPU handles only");
+    if (n > h->particles_cap) {
+        if (h->d_particles) cudaFree(h->d_particles);
+        if (h->d_alive) cudaFree(h->d_alive);
+        h->d_particles = nullptr; h->d_alive = nullptr; h->particles_cap = 0;
+        const size_t cap = n + n / 2 + 1024;
+        CK(cudaMalloc(&h->d_particles, cap * sizeof(fb_particle_dev)));
+        CK(cudaMalloc(&h->d_alive, cap * sizeof(int)));
+        h->particles_cap = cap;
+    }
+    h->h_alive.resize(n);
+    CK(cudaMemcpyAsync(h->d_particles, particles, n * sizeof(fb_particle), cudaMemcpyHostToDevice, h->stream));
+    k_advect_particles<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->d_particles,
+                                                                          h->d_alive, n, dt, h->cfg.h, h->d_bad);
+    CKL("k_advect_particles");
+    CK(cudaMemcpyAsync(particles, h->d_particles, n * sizeof(fb_particle), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_alive.data(), h->d_alive, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    size_t a = 0;
+    for (size_t k = 0; k < n; k++)
+        if (h->h_alive[k]) { if (a != k) particles[a] = particles[k]; a++; }
+    *n_alive = a;
     return FB_OK;
 }
 

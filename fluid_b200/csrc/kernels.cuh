@@ -840,3 +840,115 @@ __global__ void k_halo_pull(HaloPull a)
     const float4 v = __ldcv(reinterpret_cast<const float4 *>(a.peer[side] + ((size_t)((1 - side) * 3 + field) * a.lines + l) * a.pitch + 4 * c4));
     *reinterpret_cast<float4 *>(a.dst[field] + (size_t)(a.recv_i[side] + l - a.i_alloc0) * a.pitch + 4 * c4) = v;
 }
+
+// ---- the frame loop either side of Simulate ------------------------
+// Draw's pixel pass (main/main.go:550-574, 620-652; main/colors.go:8-84) and advectParticles
+// (main/main.go:512-546) on the device, so that a frame is pixels and particle positions instead of
+// float fields plus two host round trips per particle.  float32 arithmetic as the Go code; the
+// float -> integer conversions follow amd64 (truncate; "integer indefinite" for NaN / out of range).
+__device__ __forceinline__ float key2f_dev(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned go_u8(float v)
+{
+    const int t = (v != v || v >= 2147483648.0f || v < -2147483648.0f) ? (int)0x80000000 : (int)v;
+    return (unsigned)t & 0xffu;
+}
+__device__ __forceinline__ unsigned pack_rgba(float r, float g, float b)
+{
+    return go_u8(255.0f * r) | (go_u8(255.0f * g) << 8) | (go_u8(255.0f * b) << 16) | 0xff000000u;
+}
+__device__ __forceinline__ unsigned sci_color(float val, float minVal, float maxVal)   // colors.go:48-84
+{
+    val = go_minf(go_maxf(val, minVal), maxVal - 0.0001f);
+    const float d = maxVal - minVal;
+    if (d <= 0.0f) val = 0.5f;
+    else { val = val - minVal; val = val / d; }
+    const float m = 0.25f;
+    const float num = floorf(val / m);
+    const float t = num * m;
+    const float s = (val - t) / m;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    if (num == 0.0f) { g = s; b = 1.0f; }
+    else if (num == 1.0f) { g = 1.0f; b = 1.0f - s; }
+    else if (num == 2.0f) { r = s; g = 1.0f; }
+    else if (num == 3.0f) { r = 1.0f; g = 1.0f - s; }
+    return pack_rgba(r, g, b);
+}
+__device__ __forceinline__ unsigned diverging_color(float val, float absMax)            // colors.go:8-46
+{
+    if (absMax < 1e-8f) return 0xffffffffu;
+    float t = val / absMax;
+    if (t > 1.0f) t = 1.0f;
+    if (t < -1.0f) t = -1.0f;
+    float r, g, b;
+    if (t >= 0.0f) { r = 1.0f; g = 1.0f - t; b = 1.0f - t; }
+    else { const float a = -t; r = 1.0f - a; g = 1.0f - a; b = 1.0f; }
+    return pack_rgba(r, g, b);
+}
+__global__ void k_minmax_set(unsigned *red, float lo, float hi) { red[0] = f2key(lo); red[1] = f2key(hi); }
+
+// 32 x 32 tile transpose: the field is [i][j] with j contiguous, the image is [NumY-1-j][i] with i
+// contiguous.  Block (32, 8).  `img` holds this rank's lines only: pixel (jj, i - ib), row length ie - ib.
+template <int DIVERGING>
+__global__ void __launch_bounds__(256)
+k_render(Grid g, const float *__restrict__ A, const float *__restrict__ S, const unsigned *__restrict__ red,
+         unsigned *__restrict__ img, int ib, int ie)
+{
+    __shared__ unsigned tile[32][33];
+    const float lo = key2f_dev(red[0]), hi = key2f_dev(red[1]);
+    const float absMax = fmaxf(fabsf(lo), fabsf(hi));          // math.Max(math.Abs, math.Abs): exact in float32
+    const int i0 = ib + blockIdx.y * 32, j0 = blockIdx.x * 32;
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int i = i0 + threadIdx.y + r, j = j0 + threadIdx.x;
+        unsigned c = 0;
+        if (i < ie && j < g.NY) {
+            const size_t a = g.at(i, j);
+            c = DIVERGING ? diverging_color(A[a], absMax) : sci_color(A[a], lo, hi);
+            if (S[a] == 0.0f) c = 0xff000000u;                  // solid cells black (main.go:564-574)
+        }
+        tile[threadIdx.y + r][threadIdx.x] = c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int i = i0 + threadIdx.x, j = j0 + threadIdx.y + r;
+        if (i < ie && j < g.NY) img[(size_t)(g.NY - 1 - j) * (ie - ib) + (i - ib)] = tile[threadIdx.x][threadIdx.y + r];
+    }
+}
+
+struct fb_particle_dev { float x, y; unsigned rgbx; float age, max_age; };
+__global__ void k_advect_particles(Grid g, const float *__restrict__ U, const float *__restrict__ V,
+                                   const float *__restrict__ S, fb_particle_dev *__restrict__ ps, int *__restrict__ alive,
+                                   size_t n, float dt, float h, int *bad)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    fb_particle_dev p = ps[t];
+    const float h1 = 1.0f / h, h2 = 0.5f * h;
+    int ok = 0;
+    p.age = p.age + dt;
+    if (!(p.age > p.max_age)) {
+        const float u1 = sample_from<0>(g, U, p.x, p.y, h, h1, h2, bad);
+        const float v1 = sample_from<1>(g, V, p.x, p.y, h, h1, h2, bad);
+        const float hd = 0.5f * dt;
+        const float mu = hd * u1, mv = hd * v1;
+        const float midX = p.x + mu, midY = p.y + mv;
+        const float u2 = sample_from<0>(g, U, midX, midY, h, h1, h2, bad);
+        const float v2 = sample_from<1>(g, V, midX, midY, h, h1, h2, bad);
+        const float du = dt * u2, dv = dt * v2;
+        p.x = p.x + du;
+        p.y = p.y + dv;
+        // int(p.X / h): truncation toward zero, so (-1, 0) maps to cell 0; NaN / huge -> MinInt64 -> dropped
+        const float qx = p.x / h, qy = p.y / h;
+        if (qx > -1.0f && qx < (float)g.NX && qy > -1.0f && qy < (float)g.NY) {
+            const int fi = (int)qx, fj = (int)qy;
+            if (fi >= g.i_alloc0 && fi < g.i_alloc0 + g.lines_alloc) ok = S[g.at(fi, fj)] != 0.0f;
+            else *bad = 1;
+        }
+    }
+    ps[t] = p;
+    alive[t] = ok;
+}

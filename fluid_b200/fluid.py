@@ -24,6 +24,11 @@ Relaxation = 1.9
 _MAXF = float(np.finfo(np.float32).max)
 
 
+# main/main.go:139-144 (`type Particle`), the layout of fb_particle
+PARTICLE_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("pad", "u1"),
+                           ("age", "<f4"), ("max_age", "<f4")])
+
+
 class ScalarField:
     """scalar_field.go:7-22."""
 
@@ -356,6 +361,40 @@ class Fluid:
         mn, mx = C.c_float(), C.c_float()
         L.check(self._h, L.lib.fb_view_end(self._h, C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
+
+    # ---- the frame loop either side of Simulate (main/main.go Draw / advectParticles) -----------
+    def Render(self, kind: int, color_range=None) -> np.ndarray:
+        """Draw's pixel pass on the device (main/main.go:550-574, 620-652; main/colors.go): the view
+        through the UI's colormap, solid cells black, as the RGBA image [NumY][NumX][4] of
+        fluidToImageIndex.  Returns the image; .last_range holds the (min, max) it was coloured with."""
+        self.flush()
+        out = np.zeros((self.NumY, self.NumX, 4), dtype=np.uint8)
+        rng = (C.c_float * 2)(*color_range) if color_range is not None else None
+        mn, mx = C.c_float(), C.c_float()
+        L.check(self._h, L.lib.fb_render(self._h, kind, out.ctypes.data, rng, C.byref(mn), C.byref(mx)))
+        self.last_range = (mn.value, mx.value)
+        return out
+
+    def render_begin(self, kind: int, out, color_range=None) -> None:
+        """Pipelined Render (fb_render_begin): `out` is a pinned uint8 array [NumY][NumX][4] or its address."""
+        self.flush()
+        addr = out if isinstance(out, int) else out.ctypes.data
+        rng = (C.c_float * 2)(*color_range) if color_range is not None else None
+        L.check(self._h, L.lib.fb_render_begin(self._h, kind, addr, rng))
+
+    def render_end(self):
+        mn, mx = C.c_float(), C.c_float()
+        L.check(self._h, L.lib.fb_render_end(self._h, C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def AdvectParticles(self, particles: np.ndarray, dt: float) -> np.ndarray:
+        """advectParticles (main/main.go:512-546) for a structured array of PARTICLE_DTYPE; returns the
+        survivors in their original order."""
+        self.flush()
+        ps = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE).copy()
+        n = C.c_size_t()
+        L.check(self._h, L.lib.fb_advect_particles(self._h, ps.ctypes.data, len(ps), dt, C.byref(n)))
+        return ps[:n.value]
 
     def Smoke(self) -> ScalarField:               # smoke.go:5
         return self._view(L.VIEW_SMOKE)

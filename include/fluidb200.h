@@ -200,6 +200,23 @@ int fb_view(fb_handle *h, int32_t kind, float *out_or_null, float *min_value, fl
  * main/main.go's draw-frame-k-while-computing-k+1 loop: Smoke() at main/main.go:247. */
 int fb_view_begin(fb_handle *h, int32_t kind, float *out);
 int fb_view_end(fb_handle *h, float *min_value, float *max_value);
+/* ---- the frame loop either side of Simulate: Draw's pixel pass and advectParticles ---------
+ * fb_render*: the view through the UI's colormap (main/colors.go:8-84: getSciValue; getDivergingColor
+ * for vorticity) with solid cells black (main/main.go:564-574), as the RGBA image Draw hands to the
+ * renderer: [NumY rows][NumX pixels][4 bytes], row jj showing fluid column NumY-1-jj
+ * (fluidToImageIndex, main/main.go:795).  `range` = {min, max} to colour with, or NULL for the view's
+ * own min / max; begin / end pipeline exactly like fb_view_begin / fb_view_end (one in flight, shared). */
+int fb_render_begin(fb_handle *h, int32_t kind, uint8_t *rgba_out, const float *range_or_null);
+int fb_render_end(fb_handle *h, float *min_value, float *max_value);
+int fb_render(fb_handle *h, int32_t kind, uint8_t *rgba_out, const float *range_or_null, float *min_value, float *max_value);
+/* advectParticles (main/main.go:512-546): age, RK2 midpoint through SampleVelocity, bounds and solid
+ * checks, for n particles in host memory, in place; survivors keep their order, *n_alive counts them. */
+typedef struct fb_particle {   /* main/main.go:139-144 */
+    float x, y;
+    uint8_t r, g, b, pad;
+    float age, max_age;
+} fb_particle;
+int fb_advect_particles(fb_handle *h, fb_particle *particles, size_t n, float dt, size_t *n_alive);
 int fb_reduce(fb_handle *h, int32_t kind, float *out);
 /* SampleVelocity (fluid.go:799-803) for n points; xy and uv are [n][2]. */
 int fb_sample_velocity(fb_handle *h, size_t n, const float *xy, float *uv);

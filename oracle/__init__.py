@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
             "fo_velocity_magnitude": (None, [P, C.c_void_p, f32p, f32p]),
             "fo_max_divergence": (C.c_float, [P]),
             "fo_sample_velocity": (None, [P, C.c_float, C.c_float, f32p, f32p]),
+            "fo_render": (None, [P, C.c_int, C.c_void_p]),
+            "fo_advect_particles": (C.c_int64, [P, C.c_void_p, C.c_int64, C.c_float]),
             "fo_apply_edits": (C.c_int, [P, C.c_void_p, C.c_int64]),
             "fo_run": (C.c_int, [P, C.c_float, C.c_int64, C.c_void_p, C.c_int64]),
             "fo_project_redblack": (C.c_float, [P, C.c_uint, C.c_float]),
@@ -358,6 +360,18 @@ class OracleFluid:
         u, v = C.c_float(), C.c_float()
         self._l.fo_sample_velocity(self._f, x, y, C.byref(u), C.byref(v))
         return u.value, v.value
+
+    def Render(self, kind):
+        """Draw's pixel pass (main/main.go:550-574, 620-652): RGBA image [NumY][NumX][4] of view `kind`."""
+        out = np.zeros((self.NumY, self.NumX, 4), dtype=np.uint8)
+        self._l.fo_render(self._f, int(kind), out.ctypes.data)
+        return out
+
+    def AdvectParticles(self, particles, dt):
+        """advectParticles (main/main.go:512-546) on a structured array (fluid_b200.PARTICLE_DTYPE)."""
+        ps = np.ascontiguousarray(particles).copy()
+        n = self._l.fo_advect_particles(self._f, ps.ctypes.data, len(ps), dt)
+        return ps[:n]
 
     def SampleVelocities(self, xy):
         xy = np.asarray(xy, dtype=np.float32).reshape(-1, 2)

@@ -981,6 +981,99 @@ void fo_sample_velocity(const fo_fluid *f, float x, float y, float *u, float *v)
     *v = sample_from(f, x, y, f->V, FO_FIELD_V);
 }
 
+/* ---- the UI's pixel pass and particle tracers (main/main.go, main/colors.go) ---------------
+ * Go converts float32 -> uint8 / int with CVTTSS2SL / CVTTSS2SQ on amd64: truncation toward zero,
+ * the "integer indefinite" value (sign bit only) for NaN and out-of-range inputs. */
+static inline uint8_t go_u8(float v)
+{
+    int32_t t = (v != v || v >= 2147483648.0f || v < -2147483648.0f) ? INT32_MIN : (int32_t)v;
+    return (uint8_t)t;
+}
+static inline int64_t go_int(float v)
+{
+    return (v != v || v >= 9223372036854775808.0f || v < -9223372036854775808.0f) ? INT64_MIN : (int64_t)v;
+}
+
+static void sci_color(float val, float minVal, float maxVal, uint8_t *px)   /* colors.go:48-84 */
+{
+    val = go_minf(go_maxf(val, minVal), maxVal - 0.0001f);
+    float d = maxVal - minVal;
+    if (d <= 0.0f) val = 0.5f;
+    else val = (val - minVal) / d;
+    const float m = 0.25f;
+    float num = (float)floor((double)(val / m));
+    float t = num * m;
+    float s = (val - t) / m;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    if (num == 0.0f) { r = 0.0f; g = s; b = 1.0f; }
+    else if (num == 1.0f) { r = 0.0f; g = 1.0f; b = 1.0f - s; }
+    else if (num == 2.0f) { r = s; g = 1.0f; b = 0.0f; }
+    else if (num == 3.0f) { r = 1.0f; g = 1.0f - s; b = 0.0f; }
+    px[0] = go_u8(255.0f * r); px[1] = go_u8(255.0f * g); px[2] = go_u8(255.0f * b); px[3] = 0xff;
+}
+
+static void diverging_color(float val, float minVal, float maxVal, uint8_t *px)   /* colors.go:8-46 */
+{
+    float absMax = (float)fmax(fabs((double)minVal), fabs((double)maxVal));
+    if (absMax < 1e-8f) { px[0] = px[1] = px[2] = 255; px[3] = 255; return; }
+    float t = val / absMax;
+    if (t > 1.0f) t = 1.0f;
+    if (t < -1.0f) t = -1.0f;
+    float r, g, b;
+    if (t >= 0.0f) { r = 1.0f; g = 1.0f - t; b = 1.0f - t; }
+    else { float a = -t; r = 1.0f - a; g = 1.0f - a; b = 1.0f; }
+    px[0] = go_u8(255.0f * r); px[1] = go_u8(255.0f * g); px[2] = go_u8(255.0f * b); px[3] = 0xff;
+}
+
+void fo_render(const fo_fluid *f, int kind, uint8_t *rgba)
+{
+    const int64_t NX = f->NumX, NY = f->NumY;
+    float *vals = NULL;
+    const float *src;
+    float mn, mx;
+    if (kind == 0) { src = f->M; fo_minmax(src, f->numCells, &mn, &mx); }
+    else if (kind == 1) { src = f->p; fo_minmax(src, f->numCells, &mn, &mx); }
+    else {
+        vals = (float *)malloc((size_t)f->numCells * sizeof(float));
+        if (kind == 2) fo_velocity_magnitude(f, vals, &mn, &mx); else fo_vorticity(f, vals, &mn, &mx);
+        src = vals;
+    }
+    for (int64_t i = 0; i < NX; i++)
+        for (int64_t jj = 0; jj < NY; jj++) {
+            const int64_t j = NY - jj - 1;
+            uint8_t *px = rgba + 4 * i + jj * 4 * NX;                  /* fluidToImageIndex, Stride = 4*NumX */
+            if (kind == 3) diverging_color(src[i * NY + j], mn, mx, px);    /* drawVorticityField */
+            else sci_color(src[i * NY + j], mn, mx, px);                    /* drawScalarField */
+            if (f->S[i * NY + j] == 0.0f) { px[0] = 0; px[1] = 0; px[2] = 0; px[3] = 0xff; }   /* main.go:564-574 */
+        }
+    free(vals);
+}
+
+int64_t fo_advect_particles(const fo_fluid *f, fo_particle *ps, int64_t n, float dt)
+{
+    const float h = f->h;
+    int64_t alive = 0;
+    for (int64_t k = 0; k < n; k++) {
+        fo_particle p = ps[k];
+        p.age += dt;
+        if (p.age > p.max_age) continue;
+        float u1, v1, u2, v2;
+        fo_sample_velocity(f, p.x, p.y, &u1, &v1);
+        float hd = 0.5f * dt;
+        float mu = hd * u1, mv = hd * v1;
+        float midX = p.x + mu, midY = p.y + mv;
+        fo_sample_velocity(f, midX, midY, &u2, &v2);
+        float du = dt * u2, dv = dt * v2;
+        p.x += du;
+        p.y += dv;
+        int64_t fi = go_int(p.x / h), fj = go_int(p.y / h);
+        if (fi < 0 || fi >= f->NumX || fj < 0 || fj >= f->NumY) continue;
+        if (f->S[fi * f->NumY + fj] == 0.0f) continue;
+        ps[alive++] = p;
+    }
+    return alive;
+}
+
 /* ---- NOT in the reference: red-black ordering of the fluid.go:196-229 update.
  * One iteration = red half-sweep ((i+j) even) then black half-sweep; within a
  * half-sweep no two updated cells share a face, so the result is independent

@@ -85,6 +85,23 @@ void fo_velocity_magnitude(const fo_fluid *f, float *vals, float *mn, float *mx)
 float fo_max_divergence(const fo_fluid *f);
 void fo_sample_velocity(const fo_fluid *f, float x, float y, float *u, float *v);
 
+/* ---- the frame loop either side of Simulate (main/main.go, main/colors.go): the UI's pixel pass and
+ * its particle tracers, restated so that the device versions (fb_render, fb_advect_particles) can be
+ * checked bit for bit.  SURVEY.md section 8(f) rank 3. */
+typedef struct fo_particle {       /* main/main.go:139-144 */
+    float x, y;
+    uint8_t r, g, b, pad;
+    float age, max_age;
+} fo_particle;
+/* advectParticles (main/main.go:512-546): ages, RK2 midpoint through SampleVelocity, bounds and
+ * solid checks; survivors are compacted in place in their original order.  Returns how many. */
+int64_t fo_advect_particles(const fo_fluid *f, fo_particle *ps, int64_t n, float dt);
+/* Draw's pixel pass (main/main.go:550-574, 620-652; colors.go:8-84): view `kind` (0 smoke, 1 pressure,
+ * 2 velocity magnitude, 3 vorticity) through getSciValue / getDivergingColor into an RGBA image of
+ * NumX x NumY pixels (row jj of the image is fluid column NumY-1-jj: fluidToImageIndex, main.go:795),
+ * solid cells painted (0,0,0,255). */
+void fo_render(const fo_fluid *f, int kind, uint8_t *rgba);
+
 /* Edit command lists with the layout of fb_edit_cmd (include/fluidb200.h): the
  * same preset description drives the oracle and the CUDA path.  Rectangles are
  * walked in lexicographic order calling the point edits above. */

@@ -348,6 +348,64 @@ def test_pipelined_view_equals_blocking_view_and_overlaps_next_step():
     g.close()
 
 
+@pytest.mark.parametrize("preset_name", ["karman", "cavity"])
+def test_render_matches_the_ui_pixel_pass(preset_name):
+    """fb_render == Draw's pixel pass (main/main.go:550-574, 620-652; main/colors.go) restated in the oracle:
+    all four views, both colormaps, solid overlay, image layout -- byte for byte."""
+    from fluid_b200 import presets, _lib as L
+    p = {"karman": presets.karman(150, 90), "cavity": presets.cavity(97, 61)}[preset_name]
+    o = developed_state(p)
+    g = gpu_clone(o, p)
+    for kind in (L.VIEW_SMOKE, L.VIEW_PRESSURE, L.VIEW_VELOCITY_MAGNITUDE, L.VIEW_VORTICITY):
+        got, want = g.Render(kind), o.Render(kind)
+        assert got.shape == (g.NumY, g.NumX, 4)
+        bad = np.argwhere((got != want).any(axis=2))
+        assert len(bad) == 0, f"kind {kind}: {len(bad)} pixels differ, first {bad[:3].tolist()}"
+    # explicit colour range (what a multi-GPU host passes after its all-reduce) and the pipelined form
+    mn, mx = g.last_range
+    out = np.zeros((g.NumY, g.NumX, 4), dtype=np.uint8)
+    g.render_begin(L.VIEW_VORTICITY, out, (mn, mx))
+    g.step(p.dt, 1, p.per_step)
+    assert g.render_end() == (mn, mx)
+    assert (out == o.Render(L.VIEW_VORTICITY)).all()
+    # degenerate ranges: a field that is constant (d <= 0 -> 0.5) and all-zero vorticity (white)
+    import fluid_b200, oracle
+    e, eo = fluid_b200.New(1.0, 6, 5, 1.0), oracle.New(1.0, 6, 5, 1.0)
+    for f in (e, eo):
+        for i in range(1, 7):
+            for j in range(1, 6):
+                f.SetSolid(i, j, False)
+    for kind in (L.VIEW_SMOKE, L.VIEW_VORTICITY):
+        assert (e.Render(kind) == eo.Render(kind)).all()
+    e.close(); g.close()
+
+
+def test_advect_particles_matches_the_ui_tracer():
+    """fb_advect_particles == advectParticles (main/main.go:512-546): ageing, RK2 midpoint through
+    SampleVelocity, bounds / solid culling, survivors in order -- bit for bit."""
+    import fluid_b200
+    from fluid_b200 import presets
+    p = presets.karman(150, 90)
+    o = developed_state(p)
+    g = gpu_clone(o, p)
+    rng = np.random.default_rng(11)
+    n = 5000
+    ps = np.zeros(n, dtype=fluid_b200.PARTICLE_DTYPE)
+    ps["x"] = rng.uniform(-0.05, (p.width + 2) * p.h + 0.05, n).astype(np.float32)     # some start outside
+    ps["y"] = rng.uniform(-0.05, (p.height + 2) * p.h + 0.05, n).astype(np.float32)
+    ps["r"], ps["g"], ps["b"] = rng.integers(0, 256, (3, n), dtype=np.uint8)
+    ps["age"] = rng.uniform(0, 2, n).astype(np.float32)
+    ps["max_age"] = rng.uniform(0.5, 3, n).astype(np.float32)                          # some expire
+    ps["x"][:3] = [np.nan, np.inf, -np.inf]
+    a, b = ps.copy(), ps.copy()
+    for _ in range(5):
+        a, b = g.AdvectParticles(a, 0.05), o.AdvectParticles(b, 0.05)
+        assert len(a) == len(b) and 0 < len(a) < n
+        assert a.tobytes() == b.tobytes()
+    assert len(g.AdvectParticles(ps[:0], 0.05)) == 0
+    g.close()
+
+
 def test_apply_force_radius_and_misc_edits_match():
     from fluid_b200 import presets
     p = presets.jet(60, 40)
