@@ -371,6 +371,46 @@ def main():
                "blocking_loop": {"value": cells_total * args.steps / sync_s, "ms_per_step": sync_s / args.steps * 1e3,
                                  "what": "same loop with the blocking fb_view after every step"}}
 
+        # ---- the frame loop's neighbours of the hot path, reported beside e2e:
+        # the same pipelined loop delivering PIXELS (Draw's colormap + solid overlay on the device, fb_render_begin/end)
+        # instead of the float field, and advectParticles for 1 M tracers (4 bilinear samples each).
+        images = [torch.empty((sim.NumX * sim.NumY * 4,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+
+        def render_loop(n):
+            sim.step(preset.dt, 1, per)
+            sim.render_begin(L.VIEW_SMOKE, images[0].data_ptr())
+            for k in range(1, n):
+                sim.step(preset.dt, 1, per)
+                sim.render_end()
+                sim.render_begin(L.VIEW_SMOKE, images[k & 1].data_ptr())
+            return sim.render_end()
+
+        render_loop(3)
+        barrier()
+        t0 = time.perf_counter()
+        render_loop(args.steps)
+        barrier()
+        render_s = time.perf_counter() - t0
+        nparts = 1 << 20
+        rng = np.random.default_rng(5)
+        parts = np.zeros(nparts, dtype=fluid_b200.PARTICLE_DTYPE)
+        parts["x"] = rng.uniform(preset.h, sim.NumX * preset.h, nparts).astype(np.float32)
+        parts["y"] = rng.uniform(preset.h, sim.NumY * preset.h, nparts).astype(np.float32)
+        parts["max_age"] = 1e9
+        sim.AdvectParticles(parts[:1024], preset.dt)
+        t0 = time.perf_counter()
+        alive = sim.AdvectParticles(parts, preset.dt)
+        parts_s = time.perf_counter() - t0
+        e2e["frame_loop_neighbours"] = {
+            "render_loop": {"value": cells_total * args.steps / render_s, "ms_per_step": render_s / args.steps * 1e3,
+                            "d2h_bytes_per_step": int(sim.NumX * sim.NumY * 4 + 8),
+                            "what": "the pipelined frame loop with fb_render_begin/end: the RGBA image of Draw "
+                                    "(colormap + solid overlay computed on the device) lands in pinned memory every step"},
+            "advect_particles": {"particles": nparts, "alive": int(len(alive)), "ms": parts_s * 1e3,
+                                 "particles_per_s": nparts / parts_s,
+                                 "what": "fb_advect_particles, host array in / out (H2D + RK2 midpoint on the device + D2H + "
+                                         "stable filter on the host)"}}
+
         # ---- the other solver on the same workload (reported, not the headline)
         other = fluid_b200.SOLVER_EXACT if solver != fluid_b200.SOLVER_EXACT else fluid_b200.SOLVER_REDBLACK_PRESSURE
         sim.Solver = other

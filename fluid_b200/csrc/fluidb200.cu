@@ -1619,8 +1619,11 @@ extern "C" int fb_render_begin(fb_handle *h, int32_t kind, uint8_t *rgba_out, co
     CK(cudaEventRecord(h->ev_snap, h->stream));
     CK(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
     // this rank's pixel columns [ib, ie) of every image row
-    CK(cudaMemcpy2DAsync(rgba_out + (size_t)ib * 4, (size_t)g.NX * 4, img, (size_t)(ie - ib) * 4, (size_t)(ie - ib) * 4,
-                         (size_t)g.NY, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (ie - ib == g.NX)      // whole image: one contiguous transfer (the 2-D form runs at ~85 % of it)
+        CK(cudaMemcpyAsync(rgba_out, img, (size_t)g.NX * g.NY * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    else
+        CK(cudaMemcpy2DAsync(rgba_out + (size_t)ib * 4, (size_t)g.NX * 4, img, (size_t)(ie - ib) * 4, (size_t)(ie - ib) * 4,
+                             (size_t)g.NY, cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaEventRecord(h->ev_view, h->copy_stream));
     h->view_in_flight = true;

@@ -334,6 +334,53 @@ func (f *Fluid) EndSmoke() ScalarField {
 	return ScalarField{NumX: f.NumX, NumY: f.NumY, values: f.frameBuf, MinValue: float32(mn), MaxValue: float32(mx)}
 }
 
+// ---- the frame loop either side of Simulate: main/'s Draw pixel pass and advectParticles ------
+
+// VizKind selects the view Render draws (main/main.go: VizSmoke, VizPressure, VizVelMag, VizVorticity).
+type VizKind int32
+
+const (
+	VizSmoke     VizKind = C.FB_VIEW_SMOKE
+	VizPressure  VizKind = C.FB_VIEW_PRESSURE
+	VizVelMag    VizKind = C.FB_VIEW_VELOCITY_MAGNITUDE
+	VizVorticity VizKind = C.FB_VIEW_VORTICITY
+)
+
+// Render replaces drawScalarField / drawVorticityField plus the solid overlay of Draw
+// (main/main.go:550-574, 620-652; main/colors.go:8-84): pix is the Pix slice of an
+// image.RGBA of NumX x NumY pixels (Stride 4*NumX); it is filled exactly as those loops fill it.
+// The colormap runs on the device, so a frame costs one 4-byte-per-cell transfer and no host pass.
+func (f *Fluid) Render(kind VizKind, pix []uint8) (minValue, maxValue float32) {
+	f.flush()
+	if len(pix) < 4*f.numCells {
+		panic("fluid: Render needs 4*NumX*NumY bytes")
+	}
+	var mn, mx C.float
+	check(f.h, C.fb_render(f.h, C.int32_t(kind), (*C.uint8_t)(unsafe.Pointer(&pix[0])), nil, &mn, &mx))
+	return float32(mn), float32(mx)
+}
+
+// Particle is main/main.go:139-144 with the memory layout of C.fb_particle.
+type Particle struct {
+	X, Y    float32
+	R, G, B uint8
+	_       uint8
+	Age     float32
+	MaxAge  float32
+}
+
+// AdvectParticles replaces the body of advectParticles (main/main.go:512-546): the slice is
+// updated in place and the survivors, in their original order, are returned.
+func (f *Fluid) AdvectParticles(ps []Particle, dt float32) []Particle {
+	f.flush()
+	if len(ps) == 0 {
+		return ps
+	}
+	var alive C.size_t
+	check(f.h, C.fb_advect_particles(f.h, (*C.fb_particle)(unsafe.Pointer(&ps[0])), C.size_t(len(ps)), C.float(dt), &alive))
+	return ps[:int(alive)]
+}
+
 // Pressure replaces pressure.go:5-24.
 func (f *Fluid) Pressure() ScalarField { return f.view(C.FB_VIEW_PRESSURE) }
 
