@@ -51,15 +51,24 @@
 #include "kernels.cuh"
 #include "advect_fused.cuh"
 
+#ifndef RQ_PAIR
+#define RQ_PAIR 1         // 1: one warp per ITERATION (red + black half sweep fused), 0: one warp per half sweep
+#endif
 #ifndef RQ_NL
-#define RQ_NL 35          // line slots
+#define RQ_NL (RQ_PAIR ? 28 : 35)   // line slots
 #endif
 #define RQ_H 16
-#define RQ_THREADS 832
+#define RQ_SW (RQ_PAIR ? 8 : 16)    // sweep warps
+#define RQ_LD0 (32 * RQ_SW)         // first loader thread (4 warps)
+#define RQ_WR0 (RQ_LD0 + 128)       // first writer thread (4 warps)
+#define RQ_P1 (RQ_WR0 + 128)        // producer 1 (TMA for the loader)
+#define RQ_P2 (RQ_P1 + 32)          // producer 2 (TMA for the writer)
+#define RQ_THREADS (RQ_P2 + 32)
+#define RQ_WROLE (RQ_SW + 1)        // hand-off role of the writer
 #define RQ_TJ_MAX 464     // multiple of 16; WL = TJ + 48 <= 512 (a lane owns 2 groups of 4 cells per line;
                           // 16-byte granules for the TMA copies of the mask)
 #ifndef RQ_STG
-#define RQ_STG 4          // staging ring depth (lines in flight through TMA)
+#define RQ_STG (RQ_PAIR ? 8 : 4)    // staging ring depth (lines in flight through TMA)
 #endif
 // shared memory at WL = 512, TJ = 464: 35 slots * WL * 9 B (q, -D0, neighbour count) = 157.5 KB, loader
 // staging RQ_STG * (WL*9 + 16) B = 18.1 KB, writer staging RQ_WSTG * TJ * 9 B = 32.6 KB, hand-off
@@ -72,7 +81,7 @@ __host__ __device__ __forceinline__ size_t rq_wstage_bytes(int TJ) { return (siz
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL, int TJ)
 {
     return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + RQ_WSTG * rq_wstage_bytes(TJ) + 8 * (RQ_STG + RQ_WSTG) +
-           8 * 18 * 64 + 16 * 8 * 4 + 64;
+           8 * (RQ_SW + 2) * 64 + 16 * 8 * 4 + 64;
 }
 
 struct RBQ {
@@ -171,17 +180,21 @@ __device__ __noinline__ void rq_wait_slow(unsigned bar, unsigned parity, int tag
 #ifndef RQ_POLL_SLEEP
 #define RQ_POLL_SLEEP 0
 #endif
+#ifndef RQ_SLEEP_IO
+#define RQ_SLEEP_IO 0      // ns the loader / writer / producer roles sleep after a failed poll
+#endif
+template <int SLEEP = RQ_POLL_SLEEP>
 __device__ __forceinline__ void rq_mbar_wait_a(unsigned bar, unsigned parity, int tag)
 {
 #pragma unroll 1
     for (int k = 0; k < 4096; k++) {
         if (rq_mbar_try_a(bar, parity)) return;
-#if RQ_POLL_SLEEP
-        __nanosleep(RQ_POLL_SLEEP);
-#endif
+        if (SLEEP > 0) __nanosleep(SLEEP);
     }
     rq_wait_slow(bar, parity, tag);
 }
+// the roles around the sweeps (loader, writer, the two TMA producers)
+__device__ __forceinline__ void rq_mbar_wait_io(unsigned bar, unsigned parity, int tag) { rq_mbar_wait_a<RQ_SLEEP_IO>(bar, parity, tag); }
 __device__ __forceinline__ void rq_mbar_wait(unsigned long long *bar, unsigned parity, int tag = 0)
 {
     rq_mbar_wait_a(rq_s32(bar), parity, tag);
@@ -270,7 +283,169 @@ __device__ __forceinline__ void rq_line(float *__restrict__ sQ, const unsigned c
 // RQ_NL lines ahead of another (the loader waits for the slot), so with RQ_RING > RQ_NL a
 // parity wait always refers to the current or the immediately preceding phase.
 #define RQ_RING 64
-#define RQ_ROLES 18
+#define RQ_ROLES (RQ_SW + 2)
+#define RQ_LAST_ROLE(nst) (RQ_PAIR ? ((nst) >> 1) : (nst))   // role whose arrivals mean "all half sweeps are past this line"
+
+// ---------------------------------------------------------------------------------------------
+// RQ_PAIR: one warp per ITERATION.  Step `rel` of the warp is the red half sweep on line rel
+// ("first") followed by the black half sweep on line rel-1 ("second"); both touch the columns of
+// the same parity A = (colour + line) & 1.  Everything `second` needs is already in registers:
+//   own  = q_old[rel-1][A]   the `dn` of first(rel), which was the `up` loaded two steps ago
+//   up   = first(rel)         computed a few instructions earlier
+//   left / right = first(rel-1), dn = first(rel-2): results of the two previous steps
+// and `first` reads only its own vector and the line above from shared memory (its `dn` and
+// left / right are the `up` vectors of the two previous steps).  Per four cell updates this is
+// 2.5 LDS.128 instead of 5, half the hand-offs per line, and 8 pipeline stages instead of 16.
+// The rotation of the carried vectors is done by swapping argument names in a loop unrolled by
+// two, so it costs no MOVs.
+struct RQPair { float4 pa[2], pb[2], fa[2], fb[2]; };
+
+template <int A>
+__device__ __forceinline__ float4 rq_update(const float4 qo, const float4 up, const float4 dn, const float4 ot, const float ox,
+                                            const float4 nd, const unsigned code, const float2 nwd2, const float2 c44,
+                                            const float *__restrict__ tw, float4 &t_out)
+{
+    // left / right neighbours of cell k: other-parity indices q0+k-1+A and q0+k+A
+    float2 l01, l23, r01, r23;
+    if (A) { l01 = make_float2(ot.x, ot.y); l23 = make_float2(ot.z, ot.w); r01 = make_float2(ot.y, ot.z); r23 = make_float2(ot.w, ox); }
+    else   { l01 = make_float2(ox, ot.x);   l23 = make_float2(ot.y, ot.z); r01 = make_float2(ot.x, ot.y); r23 = make_float2(ot.z, ot.w); }
+    // nb = ((q[i-1,j] + q[i+1,j]) + q[i,j-1]) + q[i,j+1];  t = nb - D0
+    const float2 nb01 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.x, dn.y), make_float2(up.x, up.y)), l01), r01);
+    const float2 nb23 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.z, dn.w), make_float2(up.z, up.w)), l23), r23);
+    const float2 t01 = __fadd2_rn(nb01, make_float2(nd.x, nd.y));
+    const float2 t23 = __fadd2_rn(nb23, make_float2(nd.z, nd.w));
+    // q' = fma(wd*rs, t, fma(-wd, q, q))
+    const float2 q01 = make_float2(qo.x, qo.y), q23 = make_float2(qo.z, qo.w);
+    const float2 b01 = __ffma2_rn(nwd2, q01, q01), b23 = __ffma2_rn(nwd2, q23, q23);
+    float2 n01, n23;
+    if (code == 0x04040404u) {                       // the common case: four interior cells
+        n01 = __ffma2_rn(c44, t01, b01);
+        n23 = __ffma2_rn(c44, t23, b23);
+    } else {                                         // walls, obstacles, domain edge: wd / s from this half sweep's table
+        n01 = __ffma2_rn(make_float2(tw[code & 7u], tw[(code >> 8) & 7u]), t01, b01);
+        n23 = __ffma2_rn(make_float2(tw[(code >> 16) & 7u], tw[(code >> 24) & 7u]), t23, b23);
+    }
+    t_out = make_float4(t01.x, t01.y, t23.x, t23.y);
+    return make_float4(n01.x, n01.y, n23.x, n23.y);
+}
+
+template <bool STATS>
+__device__ __forceinline__ void rq_stat(const float4 qo, const float4 t, const unsigned code, int lj0, bool row_owned, int TJ, float &mymax)
+{
+    if (!STATS) return;
+    const float qv[4] = { qo.x, qo.y, qo.z, qo.w }, tv[4] = { t.x, t.y, t.z, t.w };
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned ns = (code >> (8 * k)) & 0xffu;
+        const int lj = lj0 + 2 * k;
+        if (ns && row_owned && lj >= RQ_H && lj < RQ_H + TJ) {
+            const float ad = fabsf(__fmaf_rn((float)ns, qv[k], -tv[k]));     // |div| before the update
+            if (ad > mymax) mymax = ad;
+        }
+    }
+}
+
+struct RQStage {
+    float *sQ; const unsigned char *sC;
+    int WQ, NDO, lane4, TJ;
+    float2 nwd1, c41, nwd2, c42;        // (-wd, -wd) and (wd/4, wd/4) of the two half sweeps
+    const float *tw1, *tw2;
+    // hand-offs: wait on the predecessor's barriers, arrive on ours; slots of lines rel-1, rel, rel+1
+    unsigned wbase, abase;
+    int lag, nproc, tag;
+    int e_dn, e_own, e_up, sl_up, ROW;
+    int i0r, i1r;                       // owned lines, relative to e0 (STATS only)
+    bool skip;
+    float mymax;
+};
+
+// One step.  P2 (in: q_old[rel-1][A], out: the `up` loaded now), P1 (q_old[rel][1-A]), F2 (in: first(rel-2),
+// out: first(rel)), F1 (first(rel-1)).  FIRST is false only for the step past the last line (line e1 is never
+// swept and reads as q = 0), SECOND only for step 0.  In pair mode a slot is always 512 columns wide, so every
+// lane owns two groups of four same-parity cells and nothing in the step is predicated.
+template <int A, bool FIRST, bool SECOND, bool STATS>
+__device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (&P2)[2], float4 (&P1)[2], float4 (&F2)[2],
+                                             const float4 (&F1)[2])
+{
+    {
+        const int w = min(rel + S.lag, S.nproc);
+        rq_mbar_wait_a(S.wbase + 8u * (unsigned)(w & (RQ_RING - 1)), (unsigned)(w >> 6) & 1u, S.tag | w);
+    }
+    __syncwarp();          // the other lanes' stores of the previous step (left / right neighbours of `second`)
+    float *const sQ = S.sQ;
+    const int own = S.e_own + A * S.WQ + S.lane4, oth = S.e_own + (1 - A) * S.WQ + S.lane4;
+    const int upo = S.e_up + A * S.WQ + S.lane4;
+    const int own2 = S.e_dn + A * S.WQ + S.lane4, oth2 = S.e_dn + (1 - A) * S.WQ + S.lane4 + (A ? 4 : -1);
+    if (!SECOND) {         // step 0: q_old[0][other parity] is the one carried vector that was never an `up`
+        P1[0] = *reinterpret_cast<const float4 *>(sQ + oth);
+        P1[1] = *reinterpret_cast<const float4 *>(sQ + oth + 128);
+    }
+    if (!S.skip) {
+        float4 qo[2], up[2], nd[2], nd2[2];
+        float ox[2], ox2[2];
+        unsigned code[2], code2[2];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int h0 = 128 * half;
+            if (FIRST) {
+                qo[half] = *reinterpret_cast<const float4 *>(sQ + own + h0);
+                up[half] = *reinterpret_cast<const float4 *>(sQ + upo + h0);
+                nd[half] = *reinterpret_cast<const float4 *>(sQ + own + h0 + S.NDO);
+                ox[half] = sQ[oth + h0 + (A ? 4 : -1)];
+                code[half] = *reinterpret_cast<const unsigned *>(S.sC + own + h0);
+            }
+            if (SECOND) {
+                nd2[half] = *reinterpret_cast<const float4 *>(sQ + own2 + h0 + S.NDO);
+                ox2[half] = sQ[oth2 + h0];
+                code2[half] = *reinterpret_cast<const unsigned *>(S.sC + own2 + h0);
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int h0 = 128 * half;
+            float4 t, fnow = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FIRST) {
+                fnow = rq_update<A>(qo[half], up[half], P2[half], P1[half], ox[half], nd[half], code[half], S.nwd1, S.c41, S.tw1, t);
+                *reinterpret_cast<float4 *>(sQ + own + h0) = fnow;
+                rq_stat<STATS>(qo[half], t, code[half], 2 * (S.lane4 + h0) + A, rel >= S.i0r && rel < S.i1r, S.TJ, S.mymax);
+            }
+            if (SECOND) {
+                const float4 snow = rq_update<A>(P2[half], fnow, F2[half], F1[half], ox2[half], nd2[half], code2[half], S.nwd2, S.c42, S.tw2, t);
+                *reinterpret_cast<float4 *>(sQ + own2 + h0) = snow;
+                rq_stat<STATS>(P2[half], t, code2[half], 2 * (S.lane4 + h0) + A, rel - 1 >= S.i0r && rel - 1 < S.i1r, S.TJ, S.mymax);
+            }
+            if (FIRST) P2[half] = up[half];
+            F2[half] = fnow;
+        }
+    }
+    rq_arrive_a(S.abase + 8u * (unsigned)(rel & (RQ_RING - 1)));
+    S.e_dn = S.e_own; S.e_own = S.e_up;
+    if (++S.sl_up == RQ_NL) { S.sl_up = 0; S.e_up = 0; } else S.e_up += S.ROW;
+}
+
+// All steps 0 .. nproc of one iteration.  A0 = column parity of the active cells at step 0; it alternates
+// from step to step, and the carried vectors swap names instead of moving (loop unrolled by two).
+template <int A0, bool STATS>
+__device__ __forceinline__ void rq_pair_stage(RQStage &S)
+{
+    float4 pa[2], pb[2], fa[2], fb[2];
+#pragma unroll
+    for (int half = 0; half < 2; half++) pa[half] = pb[half] = fa[half] = fb[half] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nproc = S.nproc;                                       // >= 2 * RQ_H + 1
+    rq_pair_step<A0, true, false, STATS>(S, 0, pa, pb, fa, fb);
+    int rel = 1;
+    for (; rel + 1 < nproc; rel += 2) {
+        rq_pair_step<1 - A0, true, true, STATS>(S, rel, pb, pa, fb, fa);
+        rq_pair_step<A0, true, true, STATS>(S, rel + 1, pa, pb, fa, fb);
+    }
+    if (rel < nproc) {
+        rq_pair_step<1 - A0, true, true, STATS>(S, rel, pb, pa, fb, fa);
+        rq_pair_step<A0, false, true, STATS>(S, rel + 1, pa, pb, fa, fb);
+    } else {
+        rq_pair_step<1 - A0, false, true, STATS>(S, rel, pb, pa, fb, fa);
+    }
+}
+
 // Every lane arrives and every lane polls: measured faster than one arrive / one poller per
 // warp (lane-0 polling adds a divergent branch + __syncwarp to every hand-off: 0.35 -> 0.59 ms).
 __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line, int lane)
@@ -279,7 +454,7 @@ __device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int 
 }
 __device__ __forceinline__ void rq_wait_line(unsigned long long *bars, int role, int line)
 {
-    rq_mbar_wait(bars + role * RQ_RING + (line & (RQ_RING - 1)), (unsigned)(line / RQ_RING) & 1u, (role << 20) | line);
+    rq_mbar_wait_io(rq_s32(bars + role * RQ_RING + (line & (RQ_RING - 1))), (unsigned)(line / RQ_RING) & 1u, (role << 20) | line);
 }
 __device__ __forceinline__ void rq_wait_warp(unsigned long long *bar, unsigned parity, int tag)
 {
@@ -319,7 +494,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     if (tid == 0) rq_debug = P.debug;
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, (role == 0 || role == 17) ? 128 : 32);  // arrivals per phase = threads of the role
+        rq_mbar_init(bars + k, (role == 0 || role == RQ_WROLE) ? 128 : 32);  // arrivals per phase = threads of the role
     }
     if (tid < RQ_STG) rq_mbar_init(full + tid, 1);
     if (tid >= 32 && tid < 32 + RQ_WSTG) rq_mbar_init(wfull + tid - 32, 1);
@@ -331,6 +506,34 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+#if RQ_PAIR
+    if (warp < RQ_SW) {
+        // ================= iteration `warp`: half sweeps 2*warp (first) and 2*warp + 1 (second) =================
+        const int t = warp;
+        if (2 * t >= nst) return;
+        const int colour = P.stage0 & 1;                     // nst and stage0 are even: a pass is whole iterations
+        RQStage S;
+        S.sQ = sQ; S.sC = sC; S.WQ = WQ; S.NDO = RQ_NL * WL; S.lane4 = 4 * lane; S.TJ = P.TJ;
+        S.nwd1 = make_float2(-P.wd[2 * t], -P.wd[2 * t]);
+        S.nwd2 = make_float2(-P.wd[2 * t + 1], -P.wd[2 * t + 1]);
+        { const float c1 = P.wd[2 * t] * 0.25f, c2 = P.wd[2 * t + 1] * 0.25f; S.c41 = make_float2(c1, c1); S.c42 = make_float2(c2, c2); }
+        S.tw1 = tblw + 8 * (2 * t); S.tw2 = tblw + 8 * (2 * t + 1);
+        // wait on the predecessor (loader: line rel+1 is loaded; iteration t-1: its step rel+2 is done, i.e. its
+        // second half sweep is past line rel+1), arrive on role 1+t for every step 0 .. nproc
+        S.wbase = rq_s32(bars + t * RQ_RING); S.abase = rq_s32(bars + (1 + t) * RQ_RING);
+        S.lag = t == 0 ? 1 : 2; S.nproc = nproc; S.tag = t << 20;
+        S.e_dn = (RQ_NL - 1) * ROW; S.e_own = 0; S.e_up = ROW; S.sl_up = 1; S.ROW = ROW;
+        S.i0r = i0c - e0; S.i1r = i1c - e0;
+        S.skip = (P.xflags & 1) != 0;
+        S.mymax = 0.0f;
+        if ((colour + e0) & 1) rq_pair_stage<1, STATS>(S); else rq_pair_stage<0, STATS>(S);
+        float mymax = S.mymax;
+        if (STATS) {
+            mymax = warp_max(mymax);
+            if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 >> 1) + t), __float_as_uint(mymax));
+        }
+    } else if (warp < RQ_SW + 4) {
+#else
     if (warp < 16) {
         // ================= half sweep `warp` =================
         const int s = warp;
@@ -373,8 +576,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 + s) >> 1), __float_as_uint(mymax));
         }
     } else if (warp < 20) {
+#endif
         // ================= loader: staging -> slot, lines e0 .. e1 =================
-        const int ld = tid - 512;
+        const int ld = tid - RQ_LD0;
         const bool active = ld < (WL >> 2);
         const int j = jr0 + 4 * ld;
         const bool col_in = active && j >= 0 && j < PIT;
@@ -389,26 +593,26 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         // zero on the ring and in solids); line e1 is loaded but never swept
         const int live_lo = max(1, g.i_alloc0) - e0;
         const int live_hi = min(min(NX - 2, g.i_alloc0 + g.lines_alloc - 2), e1 - 1) - e0;
-        const unsigned b_self = rq_s32(bars), b_writer = rq_s32(bars + 17 * RQ_RING), b_last = rq_s32(bars + nst * RQ_RING);
+        const unsigned b_self = rq_s32(bars), b_writer = rq_s32(bars + RQ_WROLE * RQ_RING), b_last = rq_s32(bars + RQ_LAST_ROLE(nst) * RQ_RING);
         const unsigned b_full = rq_s32(full);
         // element offset of this thread's cells in slot 0; staging offsets of lines rel and rel+1
         int e_row = 2 * ld, sl = 0;
         int st0 = 0, st1 = (RQ_STG > 1) ? 1 : 0;
         unsigned par1 = 0;                                   // phase parity of staging slot st1's current use
-        rq_mbar_wait_a(b_full, 0u, (30 << 20));              // line 0 has landed
+        rq_mbar_wait_io(b_full, 0u, (30 << 20));              // line 0 has landed
         for (int rel = 0; rel <= nproc; rel++) {
             // slot(rel) last held line y-1 with y = rel-NL+1; its last readers work on line y: the writer
             // if y is an owned line, otherwise the last half sweep
             const int y = rel - RQ_NL + 1;
             if (y >= 0) {
                 const unsigned bb = (y >= RQ_H && y <= last_owned) ? b_writer : b_last;
-                rq_mbar_wait_a(bb + 8u * (unsigned)(y & (RQ_RING - 1)), (unsigned)(y >> 6) & 1u, (17 << 20) | y);
+                rq_mbar_wait_io(bb + 8u * (unsigned)(y & (RQ_RING - 1)), (unsigned)(y >> 6) & 1u, (RQ_WROLE << 20) | y);
             }
             float d[4] = {0.f, 0.f, 0.f, 0.f};
             unsigned code = 0;
             // line rel+1 must have landed too (the producer stages every line 0 .. nproc); line rel was
             // waited for one iteration ago
-            if (rel < nproc) rq_mbar_wait_a(b_full + 8u * (unsigned)st1, par1, (31 << 20) | rel);
+            if (rel < nproc) rq_mbar_wait_io(b_full + 8u * (unsigned)st1, par1, (31 << 20) | rel);
             if (rel >= live_lo && rel <= live_hi && col_in) {
                 const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
                 const float *stU = reinterpret_cast<const float *>(s0) + 4 * ld, *stV = stU + WL;
@@ -439,18 +643,18 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             st0 = st1;
             if (++st1 == RQ_STG) { st1 = 0; par1 ^= 1u; }
         }
-    } else if (warp < 24) {
+    } else if (warp < RQ_SW + 8) {
         // ================= writer: owned lines -> U, V, p =================
         // U0, V0 and the mask of the line come from the writer's own TMA staging ring (second
         // producer below).  They were fetched through registers before: the re-read misses L2 more
         // often than not (ncu: 35 % read hit rate) and the register ring did not survive code
         // generation, so every line paid a DRAM round trip (74 % of the writer's stall samples).
-        const int st = tid - 640;
+        const int st = tid - RQ_WR0;
         const bool active = st < (P.TJ >> 2);
         const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
         const bool col_ok = active && w_j < NY && !(P.xflags & 2);
         const bool full4 = w_j + 3 < NY;
-        const unsigned b_self = rq_s32(bars + 17 * RQ_RING), b_last = rq_s32(bars + nst * RQ_RING), b_wfull = rq_s32(wfull);
+        const unsigned b_self = rq_s32(bars + RQ_WROLE * RQ_RING), b_last = rq_s32(bars + RQ_LAST_ROLE(nst) * RQ_RING), b_wfull = rq_s32(wfull);
         // only owned lines are written, but the hand-off phases count every line: arrive for the halo lines first
         for (int rel = 0; rel < i0c - e0; rel++) rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));
         int sl = (i0c - e0) % RQ_NL;
@@ -466,8 +670,11 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const float cp = P.cp;
         for (int r = i0c; r < i1c; r++) {
             const int rel = r - e0;
-            rq_mbar_wait_a(b_last + 8u * (unsigned)(rel & (RQ_RING - 1)), (unsigned)(rel >> 6) & 1u, (nst << 20) | rel);   // last half sweep is past line r
-            rq_mbar_wait_a(b_wfull + 8u * (unsigned)ws, wpar, (32 << 20) | rel);     // U0, V0, mask of line r have landed
+            {   // the last half sweep is past line r (RQ_PAIR: the last iteration has finished its step rel+1)
+                const int wl = rel + RQ_PAIR;
+                rq_mbar_wait_io(b_last + 8u * (unsigned)(wl & (RQ_RING - 1)), (unsigned)(wl >> 6) & 1u, (nst << 20) | rel);
+            }
+            rq_mbar_wait_io(b_wfull + 8u * (unsigned)ws, wpar, (32 << 20) | rel);     // U0, V0, mask of line r have landed
             if (col_ok) {
                 const float4 u = *reinterpret_cast<const float4 *>(sb);
                 const float4 v = *reinterpret_cast<const float4 *>(sb + oV);
@@ -530,7 +737,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             if (++ws == RQ_WSTG) { ws = 0; wpar ^= 1u; sb = wstg + 16 * st; } else sb += WSTGB;
             o += PIT;
         }
-    } else if (tid == 800) {
+    } else if (tid == RQ_P2) {
         // ================= second producer: U0, V0, mask of the owned lines for the writer =================
         const int c0 = strip * P.TJ;                                          // first column the writer owns
         const int nc = min(P.TJ, PIT - c0);                                   // multiple of 16 (pitch % 32 == 0)
@@ -541,7 +748,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const unsigned char *gM = P.mask + o0;
         int ws = 0;
         for (int r = i0c; r < i1c; r++) {
-            if (r - i0c >= RQ_WSTG) rq_wait_line(bars, 17, r - RQ_WSTG - e0);   // the writer is done with this stage
+            if (r - i0c >= RQ_WSTG) rq_wait_line(bars, RQ_WROLE, r - RQ_WSTG - e0);   // the writer is done with this stage
             unsigned char *sb = wstg + ws * WSTGB;
             if (!skip) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -555,7 +762,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             gU += PIT; gV += PIT; gM += PIT;
             if (++ws == RQ_WSTG) ws = 0;
         }
-    } else if (tid == 768) {
+    } else if (tid == RQ_P1) {
         // ================= producer: TMA bulk copies into the staging ring =================
         // line rel goes to staging slot rel % RQ_STG once the loader is past line rel - RQ_STG
         // (the loader reads staging slot(rel) for lines rel-1 and rel).  One thread: everything
@@ -588,8 +795,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 if (rel > nproc) break;
                 if (rel >= RQ_STG) {
                     const int w = rel - RQ_STG;
-                    rq_mbar_wait(reinterpret_cast<unsigned long long *>(__cvta_shared_to_generic(lbase + 8u * (unsigned)(w & (RQ_RING - 1)))),
-                                 (unsigned)(w / RQ_RING) & 1u, w);
+                    rq_mbar_wait_io(lbase + 8u * (unsigned)(w & (RQ_RING - 1)), (unsigned)(w / RQ_RING) & 1u, w);
                 }
                 if (rel >= relA && rel < relB) {
                     // order prior generic-proxy reads of this staging slot before the async-proxy writes
