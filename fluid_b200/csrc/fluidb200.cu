@@ -925,7 +925,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             const double score = util / overhead / waves;
             if (score > best) { best = score; TJ = tj; nstrips = nstr; chunk = ch; nchunks = nch; }
         }
-        WL = RQ_PAIR ? 512 : TJ + 2 * RQ_H + 16;   // pair mode: full-width slots, no per-lane predicates in the sweeps
+        WL = RQ_WL;
         if (!h->rbq_attr_set) {
             CK(cudaFuncSetAttribute(k_rbq_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CK(cudaFuncSetAttribute(k_rbq_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -14,74 +14,85 @@
 // checked bit for bit against its own CPU restatement fo_project_redblack_q.
 //
 // Structure: a CTA owns `chunk` lines x TJ columns (+16-cell halo, recomputed).  Lines
-// (constant i, contiguous in j) stream through a ring of 35 slots in 223 KB of shared
-// memory.  26 warps form a software pipeline WITHOUT block-wide barriers:
-//   thread 768   producer 1: TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the U, V,
-//                mask segments of a line into a 4-deep staging ring, 4 lines ahead of the loader
-//   warps 16-19  loader: staging -> -D0, neighbour count (bits 5-7 of the mask byte), q = 0 in slot(L)
-//   warp  s<16   half sweep s (colour s&1): may process line r once its predecessor
-//                (loader for s=0, warp s-1 otherwise) has finished line r+1
-//   thread 800   producer 2: TMA bulk copies of U0, V0, mask of the OWNED columns of the owned
-//                lines into an 8-deep ring for the writer
-//   warps 20-23  writer: slot(r), slot(r-1) + U0, V0, mask from its ring -> U, V, p in global
-// Hand-offs are per-line mbarriers (64 per role; every lane of the role arrives, every lane of
-// the successor polls with try_wait); the loader reuses a slot once the writer (or, for halo
-// lines, the last half sweep) is past it.  Waits are bounded: a pipeline that stops latches a
-// debug record and the host returns FB_ERR_CUDA instead of hanging the GPU.
-// Even and odd columns live in separate arrays so one colour is contiguous: a lane
-// updates 2 x 4 consecutive same-colour cells with LDS.128 / STS.128 and packed
-// FADD2 / FFMA2 (sm_100a fp32x2, bit-identical to the scalar operations).
+// (constant i, contiguous in j) stream through a ring of RQ_NL slots in shared memory
+// (q, -D0, neighbour count: 9 B per cell, 512 columns per slot).  The warps form a software
+// pipeline WITHOUT block-wide barriers:
+//   producer 1   one thread: TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the U, V,
+//                mask segments of a line into an RQ_STG-deep staging ring, ahead of the loader
+//   loader       4 warps, line-interleaved (warp k: lines k, k+4, ...): staging -> -D0, neighbour
+//                count (bits 5-7 of the mask byte), q = 0 in slot(line)
+//   stage t < 8  ITERATION t, RQ_SPLIT warps side by side.  Step `rel` is the red half sweep on
+//                line rel ("first") followed by the black half sweep on line rel-1 ("second");
+//                both touch the columns of one parity.  Everything `second` needs is in
+//                registers: its own vector is the `dn` of `first` (the `up` loaded two steps ago),
+//                its `up` is the result of `first`, left / right and `dn` are the results of the
+//                two previous steps; `first` reads only its own vector and the line above.  A
+//                stage may run step rel once its predecessor has finished step rel+2.
+//   producer 2   one thread: TMA bulk copies of U0, V0, mask of the OWNED columns of the owned
+//                lines into an RQ_WSTG-deep ring for the writer
+//   writer       4 warps, line-interleaved: slot(r), slot(r-1) + U0, V0, mask -> U, V, p in global
+// Hand-offs are PROGRESS COUNTERS in shared memory (one per warp: "steps / lines I have
+// finished"), published by lane 0 with st.release after a __syncwarp and polled by every lane of
+// the consumer with ld.acquire: a poll is an LDS (~30 cycles).  Only the TMA completions are
+// mbarriers.  Waits are bounded: a pipeline that stops latches a debug record and the host
+// returns FB_ERR_CUDA instead of hanging the GPU.
+// Even and odd columns live in separate arrays so one colour is contiguous: a lane updates 4
+// consecutive same-colour cells per group with LDS.128 / STS.128 and packed FADD2 / FFMA2
+// (sm_100a fp32x2, bit-identical to the scalar operations).
 //
 // Why this shape (ncu, 4098^2, 8 iterations; time of the solve):
 //   face form (rb_fused.cuh), ~110 instructions per cell update, issue-bound          1.11 ms
 //   pressure form, one __syncthreads per line (barrier = 3.4 of 9 stall cycles)       0.47
-//   warp-specialised roles with mbarrier hand-offs, strips x chunks = one wave        0.31
-//   writer inputs through TMA: its re-read of U0, V0 missed L2 two times in three and
-//   the register prefetch ring did not survive code generation (74 % of the writer's
-//   stall samples sat on the first use of those loads)                                0.226
+//   one warp per half sweep, per-line mbarrier hand-offs, strips x chunks = one wave  0.31
+//   writer inputs through TMA (its re-read of U0, V0 missed L2 two times in three)    0.226
 //   neighbour counts baked into the mask, lean loader / writer loops                  0.211
-// Now issue slots are 73 % and shared-memory wavefronts 74 % busy, DRAM 25 %.  Measured and NOT
-// adopted: one arrive per warp instead of 32 (no change); a 2-instruction poll loop (0.224:
-// try_wait is a shared-memory operation, faster polling takes wavefronts from the sweeps);
-// nanosleep after a failed poll (no change); 37 / 40 ring slots, 8-deep loader staging (no
-// change); re-reading the neighbour vectors instead of carrying them (0.231: LSU pipe 79 %);
-// turbulence fused into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2); four
-// lines in flight per loader / writer warp (0.47).
+//   one warp per iteration (two half sweeps fused, neighbours carried in registers)   0.208
+//   What bounded all of these was not instructions but the LATENCY of a hand-off: with every
+//   role's work switched off (FLUIDB200_RBQ_X=31) the mbarrier skeleton alone took 0.077 ms --
+//   mbarrier.try_wait costs ~115 cycles per poll and each line crosses 10 hand-offs inside a
+//   ring that is only 11 lines deeper than the pipeline.  Sleeping pollers changed nothing.
+//   line-interleaved loader / writer warps (four line periods per line)               0.223 (floor 0.124 -> 0.083)
+//   two warps per stage (half the columns each)                                       0.192
+//   progress counters instead of mbarriers: see profiles/
+// Measured and NOT adopted: one arrive per warp instead of 32 (no change); 2-instruction poll loop
+// (slower); nanosleep after a failed poll (no change); deeper rings or staging (no change);
+// re-reading the neighbour vectors instead of carrying them (LSU pipe 79 %); turbulence fused
+// into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2).
 #pragma once
 #include "kernels.cuh"
 #include "advect_fused.cuh"
 
-#ifndef RQ_PAIR
-#define RQ_PAIR 1         // 1: one warp per ITERATION (red + black half sweep fused), 0: one warp per half sweep
-#endif
 #ifndef RQ_NL
-#define RQ_NL (RQ_PAIR ? 28 : 35)   // line slots
+#define RQ_NL 28          // line slots
 #endif
 #define RQ_H 16
-#define RQ_SW (RQ_PAIR ? 8 : 16)    // sweep warps
-#define RQ_LD0 (32 * RQ_SW)         // first loader thread (4 warps)
-#define RQ_WR0 (RQ_LD0 + 128)       // first writer thread (4 warps)
-#define RQ_P1 (RQ_WR0 + 128)        // producer 1 (TMA for the loader)
-#define RQ_P2 (RQ_P1 + 32)          // producer 2 (TMA for the writer)
+#define RQ_NIT 8          // iterations per pass = pipeline stages
+#ifndef RQ_SPLIT
+#define RQ_SPLIT 2        // warps per stage (1 or 2): a line is 2 groups of 128 same-parity cells, 4 per lane
+#endif
+#define RQ_Q (2 / RQ_SPLIT)         // groups per sweep warp
+#define RQ_SW (RQ_NIT * RQ_SPLIT)   // sweep warps
+#define RQ_LW 4           // loader warps (line-interleaved)
+#define RQ_WW 4           // writer warps (line-interleaved)
+#define RQ_P1 (32 * (RQ_SW + RQ_LW + RQ_WW))   // producer 1 (TMA for the loader)
+#define RQ_P2 (RQ_P1 + 32)                      // producer 2 (TMA for the writer)
 #define RQ_THREADS (RQ_P2 + 32)
-#define RQ_WROLE (RQ_SW + 1)        // hand-off role of the writer
-#define RQ_TJ_MAX 464     // multiple of 16; WL = TJ + 48 <= 512 (a lane owns 2 groups of 4 cells per line;
-                          // 16-byte granules for the TMA copies of the mask)
+#define RQ_WL 512         // columns per slot, whatever TJ is: every lane of a sweep always owns its groups of four cells
+#define RQ_TJ_MAX 464     // multiple of 16; TJ + 2 * RQ_H + 16 <= RQ_WL (16-byte granules for the TMA copies of the mask)
 #ifndef RQ_STG
-#define RQ_STG (RQ_PAIR ? 8 : 4)    // staging ring depth (lines in flight through TMA)
+#define RQ_STG 8          // staging ring depth (lines in flight through TMA); power of two
 #endif
-// shared memory at WL = 512, TJ = 464: 35 slots * WL * 9 B (q, -D0, neighbour count) = 157.5 KB, loader
-// staging RQ_STG * (WL*9 + 16) B = 18.1 KB, writer staging RQ_WSTG * TJ * 9 B = 32.6 KB, hand-off
-// mbarriers 9.1 KB, wd/s table 0.5 KB: 217.8 KB of the 227 KB a CTA may have
-__host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
 #ifndef RQ_WSTG
-#define RQ_WSTG 8         // writer staging ring depth
+#define RQ_WSTG 8         // writer staging ring depth; power of two
 #endif
+// shared memory at TJ = 464: 28 slots * 512 * 9 B (q, -D0, neighbour count) = 126 KB, loader staging
+// 8 * (512*9 + 16) B = 36.1 KB, writer staging 8 * 464 * 9 B = 32.6 KB, mbarriers, wd/s table, counters: 196 KB
+__host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
 __host__ __device__ __forceinline__ size_t rq_wstage_bytes(int TJ) { return (size_t)TJ * 9; }   // U0, V0, mask of TJ columns
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL, int TJ)
 {
     return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + RQ_WSTG * rq_wstage_bytes(TJ) + 8 * (RQ_STG + RQ_WSTG) +
-           8 * (RQ_SW + 2) * 64 + 16 * 8 * 4 + 64;
+           8 * (RQ_NIT + 2) * 64 + 16 * 8 * 4 + 64;
 }
 
 struct RBQ {
@@ -96,7 +107,7 @@ struct RBQ {
     int TJ, WL, chunk, ib, ie;
     unsigned *stats;             // per-iteration max |div| (only when STATS)
     int *debug;                  // [0] != 0: a pipeline wait timed out, [1..5] say which
-    int xflags;                  // experiments (FLUIDB200_RBQ_X): 1 skip sweeps, 2 skip writer I/O, 4 skip TMA
+    int xflags;                  // experiments (FLUIDB200_RBQ_X): 1 skip sweeps, 2 skip writer I/O, 4 skip TMA, 8 / 16 skip the loader's reads / stores
     const float *noiseU, *noiseV;
     float turb;
 };
@@ -110,58 +121,51 @@ __device__ __forceinline__ void rq_mbar_expect_tx(unsigned long long *bar, unsig
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rq_s32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void rq_arrive_a(unsigned bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void rq_mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rq_s32(bar)) : "memory");
 }
-// no ordering of the thread's other memory operations: for roles that only READ the slots they hand back
-__device__ __forceinline__ void rq_mbar_arrive_relaxed(unsigned long long *bar)
+__device__ __forceinline__ void rq_arrive_a(unsigned bar)
 {
-    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(rq_s32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-#ifndef RQ_WAIT_HINT
-#define RQ_WAIT_HINT 0      // ns the hardware may suspend a failed try_wait (0: its default)
-#endif
 __device__ __forceinline__ bool rq_mbar_try_a(unsigned bar, unsigned parity)
 {
     unsigned ok;
-#if RQ_WAIT_HINT
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(RQ_WAIT_HINT) : "memory");
-#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-#endif
     return ok != 0;
 }
-// Bounded wait: a pipeline that stops making progress must never hang the GPU.  After
-// ~2^21 failed polls (hundreds of milliseconds) the first waiter records who waited for
-// what in P.debug and every waiter falls through; the host turns the flag into an error.
-// The polling loop is kept to try_wait + branch (4 polls per trip): the kernel is
-// issue-bound and spinning warps share the schedulers with the warps they wait for.
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void rq_tma_load(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- hand-offs -----------------------------------------------------------------------------------
+// Roles: 0 = loader, 1 + t = stage t, RQ_WROLE = writer.  Every role has a ring of RQ_RING mbarriers, one per
+// line / step (line r uses barrier r % RQ_RING, phase parity (r / RQ_RING) & 1); every lane of the warp(s)
+// that own the line arrives, every lane of a consumer polls with try_wait.  Each role arrives for EVERY line
+// 0 .. nproc, and no role can be more than RQ_NL lines ahead of another (the loader waits for the slot), so
+// with RQ_RING > 2 * RQ_NL a parity wait always refers to the current or the immediately preceding phase.
+#define RQ_RING 64
+#define RQ_ROLES (RQ_NIT + 2)
+#define RQ_WROLE (RQ_NIT + 1)
+// Bounded waits: a pipeline that stops making progress must never hang the GPU.  After ~2^21 failed polls
+// (hundreds of milliseconds) the first waiter records who waited for what in P.debug and every waiter
+// falls through; the host turns the flag into an error.
 __device__ int *rq_debug;   // set per launch (RBQ::debug)
 __device__ __noinline__ void rq_wait_slow(unsigned bar, unsigned parity, int tag)
 {
     for (unsigned trip = 0;; trip++) {
 #pragma unroll 1
-        for (int k = 0; k < 256; k++) {
+        for (int k = 0; k < 1024; k++)
             if (rq_mbar_try_a(bar, parity)) return;
-            if (rq_mbar_try_a(bar, parity)) return;
-            if (rq_mbar_try_a(bar, parity)) return;
-            if (rq_mbar_try_a(bar, parity)) return;
-        }
         int *d = rq_debug;
         if (d && *reinterpret_cast<volatile int *>(d) != 0) return;         // someone already gave up: drain
         if (trip > (1u << 11)) {
@@ -173,133 +177,27 @@ __device__ __noinline__ void rq_wait_slow(unsigned bar, unsigned parity, int tag
         }
     }
 }
-// Polling loop.  A waiting warp shares its scheduler AND the shared-memory pipe (try_wait is a
-// shared-memory operation) with the warps it waits for; measured at 4098^2, 8 iterations:
-// 7-instruction poll 211 us, 2-instruction poll 224 us (more polls per microsecond, not fewer).
-// RQ_POLL_SLEEP > 0 inserts a nanosleep after every failed poll.
-#ifndef RQ_POLL_SLEEP
-#define RQ_POLL_SLEEP 0
-#endif
-#ifndef RQ_SLEEP_IO
-#define RQ_SLEEP_IO 0      // ns the loader / writer / producer roles sleep after a failed poll
-#endif
-template <int SLEEP = RQ_POLL_SLEEP>
-__device__ __forceinline__ void rq_mbar_wait_a(unsigned bar, unsigned parity, int tag)
+// try_wait suspends the warp in hardware for a while (~100 cycles per poll), which is what keeps the pollers
+// off the shared-memory pipe: polling a counter with LDS instead (one wavefront every ~40 cycles per waiting
+// warp) was measured SLOWER (0.224 against 0.192 ms), and sleeping between polls changes nothing.
+__device__ __forceinline__ void rq_wait_a(unsigned bar, unsigned parity, int tag)
 {
 #pragma unroll 1
-    for (int k = 0; k < 4096; k++) {
+    for (int k = 0; k < 4096; k++)
         if (rq_mbar_try_a(bar, parity)) return;
-        if (SLEEP > 0) __nanosleep(SLEEP);
-    }
     rq_wait_slow(bar, parity, tag);
 }
-// the roles around the sweeps (loader, writer, the two TMA producers)
-__device__ __forceinline__ void rq_mbar_wait_io(unsigned bar, unsigned parity, int tag) { rq_mbar_wait_a<RQ_SLEEP_IO>(bar, parity, tag); }
-__device__ __forceinline__ void rq_mbar_wait(unsigned long long *bar, unsigned parity, int tag = 0)
+// line / step `line` of the role whose ring starts at `ring`
+__device__ __forceinline__ void rq_wait_line(unsigned ring, int line, int tag)
 {
-    rq_mbar_wait_a(rq_s32(bar), parity, tag);
+    rq_wait_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)), (unsigned)(line >> 6) & 1u, tag | line);
 }
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void rq_tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+__device__ __forceinline__ void rq_done_line(unsigned ring, int line)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(rq_s32(dst)), "l"(src), "r"(bytes), "r"(rq_s32(bar)) : "memory");
+    rq_arrive_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)));
 }
 
-// One line of one half sweep: the active cells have column parity A.  e_own / e_up / e_dn are
-// the element offsets of the three slots, NDO the distance from q to -D0 of the same cell.
-// Carried across consecutive lines of one half sweep (registers): the `up` vector of line r is
-// the other-parity vector of line r+1, and the other-parity vector of line r is the `down`
-// vector of line r+1 (nobody writes them in between).  Shared-memory wavefronts are as scarce
-// as issue slots here (ncu: 79 % of the LSU data pipe without the carry, 38 % with it).
-struct RQCarry { float4 up[2], ot[2]; };
-template <int A, bool STATS>
-__device__ __forceinline__ void rq_line(float *__restrict__ sQ, const unsigned char *__restrict__ sC, int e_own, int e_up,
-                                        int e_dn, int WQ, int NDO, int lane4, float wd, float c4, bool row_owned, int TJ,
-                                        float &mymax, const float *__restrict__ tw, RQCarry &cy, bool have)
-{
-    const float2 nwd2 = make_float2(-wd, -wd);
-    const float2 c44 = make_float2(c4, c4);               // wd * (1/s) for a cell with four fluid neighbours
-    const int own = e_own + A * WQ + lane4, oth = e_own + (1 - A) * WQ + lane4;
-    const int upo = e_up + A * WQ + lane4, dno = e_dn + A * WQ + lane4;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int h0 = 128 * half;
-        if (lane4 + h0 >= WQ) continue;
-        float *qown = sQ + own + h0;
-        const float4 qo = *reinterpret_cast<const float4 *>(qown);
-        const float4 up = *reinterpret_cast<const float4 *>(sQ + upo + h0);
-#ifdef RQ_NO_CARRY
-        const float4 dn = *reinterpret_cast<const float4 *>(sQ + dno + h0);
-        const float4 ot = *reinterpret_cast<const float4 *>(sQ + oth + h0);
-#else
-        const float4 dn = have ? cy.ot[half] : *reinterpret_cast<const float4 *>(sQ + dno + h0);
-        const float4 ot = have ? cy.up[half] : *reinterpret_cast<const float4 *>(sQ + oth + h0);
-        cy.up[half] = up;
-        cy.ot[half] = ot;
-#endif
-        const float ox = sQ[oth + h0 + (A ? 4 : -1)];
-        const float4 nd = *reinterpret_cast<const float4 *>(qown + NDO);           // -D0
-        const unsigned code = *reinterpret_cast<const unsigned *>(sC + own + h0);  // fluid-neighbour counts, 0 = skip
-        // left / right neighbours of cell k: other-parity indices q0+k-1+A and q0+k+A
-        float2 l01, l23, r01, r23;
-        if (A) { l01 = make_float2(ot.x, ot.y); l23 = make_float2(ot.z, ot.w); r01 = make_float2(ot.y, ot.z); r23 = make_float2(ot.w, ox); }
-        else   { l01 = make_float2(ox, ot.x);   l23 = make_float2(ot.y, ot.z); r01 = make_float2(ot.x, ot.y); r23 = make_float2(ot.z, ot.w); }
-        // nb = ((q[i-1,j] + q[i+1,j]) + q[i,j-1]) + q[i,j+1];  t = nb - D0
-        const float2 nb01 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.x, dn.y), make_float2(up.x, up.y)), l01), r01);
-        const float2 nb23 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.z, dn.w), make_float2(up.z, up.w)), l23), r23);
-        const float2 t01 = __fadd2_rn(nb01, make_float2(nd.x, nd.y));
-        const float2 t23 = __fadd2_rn(nb23, make_float2(nd.z, nd.w));
-        // q' = fma(wd*rs, t, fma(-wd, q, q))
-        const float2 q01 = make_float2(qo.x, qo.y), q23 = make_float2(qo.z, qo.w);
-        const float2 b01 = __ffma2_rn(nwd2, q01, q01), b23 = __ffma2_rn(nwd2, q23, q23);
-        float2 n01, n23;
-        if (code == 0x04040404u) {                       // the common case: four interior cells
-            n01 = __ffma2_rn(c44, t01, b01);
-            n23 = __ffma2_rn(c44, t23, b23);
-        } else {                                         // walls, obstacles, domain edge: wd / s from this half sweep's table
-            n01 = __ffma2_rn(make_float2(tw[code & 7u], tw[(code >> 8) & 7u]), t01, b01);
-            n23 = __ffma2_rn(make_float2(tw[(code >> 16) & 7u], tw[(code >> 24) & 7u]), t23, b23);
-        }
-        *reinterpret_cast<float4 *>(qown) = make_float4(n01.x, n01.y, n23.x, n23.y);
-        if (STATS) {
-            const float qv[4] = { qo.x, qo.y, qo.z, qo.w }, tv[4] = { t01.x, t01.y, t23.x, t23.y };
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned ns = (code >> (8 * k)) & 0xffu;
-                const int lj = 2 * (lane4 + h0 + k) + A;
-                if (ns && row_owned && lj >= RQ_H && lj < RQ_H + TJ) {
-                    const float ad = fabsf(__fmaf_rn((float)ns, qv[k], -tv[k]));
-                    if (ad > mymax) mymax = ad;
-                }
-            }
-        }
-    }
-}
-
-// hand-off barriers: role 0 = loader, 1+s = half sweep s, 17 = writer; RQ_RING barriers per
-// role, one per line (line r uses barrier r % RQ_RING, phase parity (r / RQ_RING) & 1).
-// Every role arrives for EVERY line 0 .. nproc in order, and no role can be more than
-// RQ_NL lines ahead of another (the loader waits for the slot), so with RQ_RING > RQ_NL a
-// parity wait always refers to the current or the immediately preceding phase.
-#define RQ_RING 64
-#define RQ_ROLES (RQ_SW + 2)
-#define RQ_LAST_ROLE(nst) (RQ_PAIR ? ((nst) >> 1) : (nst))   // role whose arrivals mean "all half sweeps are past this line"
-
-// ---------------------------------------------------------------------------------------------
-// RQ_PAIR: one warp per ITERATION.  Step `rel` of the warp is the red half sweep on line rel
-// ("first") followed by the black half sweep on line rel-1 ("second"); both touch the columns of
-// the same parity A = (colour + line) & 1.  Everything `second` needs is already in registers:
-//   own  = q_old[rel-1][A]   the `dn` of first(rel), which was the `up` loaded two steps ago
-//   up   = first(rel)         computed a few instructions earlier
-//   left / right = first(rel-1), dn = first(rel-2): results of the two previous steps
-// and `first` reads only its own vector and the line above from shared memory (its `dn` and
-// left / right are the `up` vectors of the two previous steps).  Per four cell updates this is
-// 2.5 LDS.128 instead of 5, half the hand-offs per line, and 8 pipeline stages instead of 16.
-// The rotation of the carried vectors is done by swapping argument names in a loop unrolled by
-// two, so it costs no MOVs.
-struct RQPair { float4 pa[2], pb[2], fa[2], fb[2]; };
-
+// ---- one cell update, four cells at a time -------------------------------------------------------
 template <int A>
 __device__ __forceinline__ float4 rq_update(const float4 qo, const float4 up, const float4 dn, const float4 ot, const float ox,
                                             const float4 nd, const unsigned code, const float2 nwd2, const float2 c44,
@@ -347,13 +245,13 @@ __device__ __forceinline__ void rq_stat(const float4 qo, const float4 t, const u
 
 struct RQStage {
     float *sQ; const unsigned char *sC;
-    int WQ, NDO, lane4, TJ;
+    int WQ, NDO, lane4, lane, TJ;
     float2 nwd1, c41, nwd2, c42;        // (-wd, -wd) and (wd/4, wd/4) of the two half sweeps
     const float *tw1, *tw2;
-    // hand-offs: wait on the predecessor's barriers, arrive on ours; slots of lines rel-1, rel, rel+1
-    unsigned wbase, abase;
-    int lag, nproc, tag;
-    int e_dn, e_own, e_up, sl_up, ROW;
+    // hand-offs: the predecessor's ring to wait on, our own to arrive on, the sibling barrier
+    unsigned pred, mine;
+    int lag, nproc, tag, bar_id;
+    int e_dn, e_own, e_up, sl_up, ROW;  // slots of lines rel-1, rel, rel+1 (element offsets)
     int i0r, i1r;                       // owned lines, relative to e0 (STATS only)
     bool skip;
     float mymax;
@@ -361,31 +259,31 @@ struct RQStage {
 
 // One step.  P2 (in: q_old[rel-1][A], out: the `up` loaded now), P1 (q_old[rel][1-A]), F2 (in: first(rel-2),
 // out: first(rel)), F1 (first(rel-1)).  FIRST is false only for the step past the last line (line e1 is never
-// swept and reads as q = 0), SECOND only for step 0.  In pair mode a slot is always 512 columns wide, so every
-// lane owns two groups of four same-parity cells and nothing in the step is predicated.
+// swept and reads as q = 0), SECOND only for step 0.
 template <int A, bool FIRST, bool SECOND, bool STATS>
-__device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (&P2)[2], float4 (&P1)[2], float4 (&F2)[2],
-                                             const float4 (&F1)[2])
+__device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (&P2)[RQ_Q], float4 (&P1)[RQ_Q], float4 (&F2)[RQ_Q],
+                                             const float4 (&F1)[RQ_Q])
 {
-    {
-        const int w = min(rel + S.lag, S.nproc);
-        rq_mbar_wait_a(S.wbase + 8u * (unsigned)(w & (RQ_RING - 1)), (unsigned)(w >> 6) & 1u, S.tag | w);
+    {   // the loader has finished line rel+1 / the previous iteration has finished its step rel+2
+        rq_wait_line(S.pred, min(rel + S.lag, S.nproc), S.tag);
     }
-    __syncwarp();          // the other lanes' stores of the previous step (left / right neighbours of `second`)
+    // the stores of the previous step by the other lanes of the stage (left / right neighbours of `second`)
+    if (RQ_SPLIT > 1) asm volatile("bar.sync %0, %1;" ::"r"(S.bar_id), "n"(32 * RQ_SPLIT) : "memory");
+    else __syncwarp();
     float *const sQ = S.sQ;
     const int own = S.e_own + A * S.WQ + S.lane4, oth = S.e_own + (1 - A) * S.WQ + S.lane4;
     const int upo = S.e_up + A * S.WQ + S.lane4;
     const int own2 = S.e_dn + A * S.WQ + S.lane4, oth2 = S.e_dn + (1 - A) * S.WQ + S.lane4 + (A ? 4 : -1);
     if (!SECOND) {         // step 0: q_old[0][other parity] is the one carried vector that was never an `up`
-        P1[0] = *reinterpret_cast<const float4 *>(sQ + oth);
-        P1[1] = *reinterpret_cast<const float4 *>(sQ + oth + 128);
+#pragma unroll
+        for (int half = 0; half < RQ_Q; half++) P1[half] = *reinterpret_cast<const float4 *>(sQ + oth + 128 * half);
     }
     if (!S.skip) {
-        float4 qo[2], up[2], nd[2], nd2[2];
-        float ox[2], ox2[2];
-        unsigned code[2], code2[2];
+        float4 qo[RQ_Q], up[RQ_Q], nd[RQ_Q], nd2[RQ_Q];
+        float ox[RQ_Q], ox2[RQ_Q];
+        unsigned code[RQ_Q], code2[RQ_Q];
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
+        for (int half = 0; half < RQ_Q; half++) {
             const int h0 = 128 * half;
             if (FIRST) {
                 qo[half] = *reinterpret_cast<const float4 *>(sQ + own + h0);
@@ -401,7 +299,7 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
             }
         }
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
+        for (int half = 0; half < RQ_Q; half++) {
             const int h0 = 128 * half;
             float4 t, fnow = make_float4(0.f, 0.f, 0.f, 0.f);
             if (FIRST) {
@@ -418,7 +316,7 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
             F2[half] = fnow;
         }
     }
-    rq_arrive_a(S.abase + 8u * (unsigned)(rel & (RQ_RING - 1)));
+    rq_done_line(S.mine, rel);
     S.e_dn = S.e_own; S.e_own = S.e_up;
     if (++S.sl_up == RQ_NL) { S.sl_up = 0; S.e_up = 0; } else S.e_up += S.ROW;
 }
@@ -428,9 +326,9 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
 template <int A0, bool STATS>
 __device__ __forceinline__ void rq_pair_stage(RQStage &S)
 {
-    float4 pa[2], pb[2], fa[2], fb[2];
+    float4 pa[RQ_Q], pb[RQ_Q], fa[RQ_Q], fb[RQ_Q];
 #pragma unroll
-    for (int half = 0; half < 2; half++) pa[half] = pb[half] = fa[half] = fb[half] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int half = 0; half < RQ_Q; half++) pa[half] = pb[half] = fa[half] = fb[half] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int nproc = S.nproc;                                       // >= 2 * RQ_H + 1
     rq_pair_step<A0, true, false, STATS>(S, 0, pa, pb, fa, fb);
     int rel = 1;
@@ -446,26 +344,11 @@ __device__ __forceinline__ void rq_pair_stage(RQStage &S)
     }
 }
 
-// Every lane arrives and every lane polls: measured faster than one arrive / one poller per
-// warp (lane-0 polling adds a divergent branch + __syncwarp to every hand-off: 0.35 -> 0.59 ms).
-__device__ __forceinline__ void rq_done(unsigned long long *bars, int role, int line, int lane)
-{
-    rq_mbar_arrive(bars + role * RQ_RING + (line & (RQ_RING - 1)));
-}
-__device__ __forceinline__ void rq_wait_line(unsigned long long *bars, int role, int line)
-{
-    rq_mbar_wait_io(rq_s32(bars + role * RQ_RING + (line & (RQ_RING - 1))), (unsigned)(line / RQ_RING) & 1u, (role << 20) | line);
-}
-__device__ __forceinline__ void rq_wait_warp(unsigned long long *bar, unsigned parity, int tag)
-{
-    rq_mbar_wait(bar, parity, tag);
-}
-
 template <bool STATS>
 __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int WL = P.WL, WQ = WL >> 1, ROW = WL;             // elements per slot in one plane
+    const int WL = RQ_WL, WQ = WL >> 1, ROW = WL;            // elements per slot in one plane
     float *sQ = reinterpret_cast<float *>(smem_raw);        // [slot][parity][q]
     float *sND = sQ + RQ_NL * WL;                            // -D0
     unsigned char *sC = reinterpret_cast<unsigned char *>(sND + RQ_NL * WL);   // fluid-neighbour count, 0 = never updated
@@ -478,6 +361,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     unsigned long long *wfull = full + RQ_STG;               // RQ_WSTG mbarriers
     unsigned long long *bars = wfull + RQ_WSTG;              // RQ_ROLES * RQ_RING hand-off mbarriers
     float *tblw = reinterpret_cast<float *>(bars + RQ_ROLES * RQ_RING);   // [half sweep][fluid neighbours] -> wd / s
+    const unsigned ring_ld = rq_s32(bars), ring_wr = rq_s32(bars + RQ_WROLE * RQ_RING);
 
     const Grid g = P.g;
     const int NX = g.NX, NY = g.NY, PIT = g.pitch;
@@ -489,148 +373,98 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
     const int jr0 = strip * P.TJ - RQ_H;
     const int e0 = i0c - RQ_H, e1 = i1c + RQ_H;               // half sweeps process lines [e0, e1); e1 is loaded too
     const int nst = P.nstages;
+    const int nit = nst >> 1;                                 // iterations of this pass (nst and stage0 are even)
     const int nproc = e1 - e0;                                // lines each half sweep passes over
+    const int own0 = i0c - e0, last_owned = (i1c - 1) - e0;   // owned lines, relative
 
     if (tid == 0) rq_debug = P.debug;
+    // arrivals per phase: every lane of the warp(s) that own the line / step
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, (role == 0 || role == RQ_WROLE) ? 128 : 32);  // arrivals per phase = threads of the role
+        rq_mbar_init(bars + k, (role == 0 || role == RQ_WROLE) ? 32 : 32 * RQ_SPLIT);
     }
-    if (tid < RQ_STG) rq_mbar_init(full + tid, 1);
-    if (tid >= 32 && tid < 32 + RQ_WSTG) rq_mbar_init(wfull + tid - 32, 1);
-    if (tid < 128) {
-        const int ns = tid & 7;
+    if (tid >= 32 && tid < 32 + RQ_STG) rq_mbar_init(full + tid - 32, 1);
+    if (tid >= 64 && tid < 64 + RQ_WSTG) rq_mbar_init(wfull + tid - 64, 1);
+    if (tid >= 128 && tid < 256) {
+        const int k = tid - 128, ns = k & 7;
         const float rs = ns == 0 ? 0.0f : (ns == 1 ? 1.0f : (ns == 2 ? 0.5f : (ns == 3 ? (1.0f / 3.0f) : 0.25f)));
-        tblw[tid] = P.wd[tid >> 3] * rs;
+        tblw[k] = P.wd[k >> 3] * rs;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-#if RQ_PAIR
     if (warp < RQ_SW) {
-        // ================= iteration `warp`: half sweeps 2*warp (first) and 2*warp + 1 (second) =================
-        const int t = warp;
-        if (2 * t >= nst) return;
-        const int colour = P.stage0 & 1;                     // nst and stage0 are even: a pass is whole iterations
+        // ================= stage t = iteration t: half sweeps 2t (first) and 2t + 1 (second) =================
+        const int t = warp / RQ_SPLIT, hw = warp % RQ_SPLIT;  // stage, and which part of the line this warp owns
+        if (t >= nit) return;
+        const int colour = P.stage0 & 1;
         RQStage S;
-        S.sQ = sQ; S.sC = sC; S.WQ = WQ; S.NDO = RQ_NL * WL; S.lane4 = 4 * lane; S.TJ = P.TJ;
+        S.sQ = sQ; S.sC = sC; S.WQ = WQ; S.NDO = RQ_NL * WL; S.lane4 = 4 * lane + 128 * RQ_Q * hw; S.lane = lane; S.TJ = P.TJ;
         S.nwd1 = make_float2(-P.wd[2 * t], -P.wd[2 * t]);
         S.nwd2 = make_float2(-P.wd[2 * t + 1], -P.wd[2 * t + 1]);
         { const float c1 = P.wd[2 * t] * 0.25f, c2 = P.wd[2 * t + 1] * 0.25f; S.c41 = make_float2(c1, c1); S.c42 = make_float2(c2, c2); }
         S.tw1 = tblw + 8 * (2 * t); S.tw2 = tblw + 8 * (2 * t + 1);
-        // wait on the predecessor (loader: line rel+1 is loaded; iteration t-1: its step rel+2 is done, i.e. its
-        // second half sweep is past line rel+1), arrive on role 1+t for every step 0 .. nproc
-        S.wbase = rq_s32(bars + t * RQ_RING); S.abase = rq_s32(bars + (1 + t) * RQ_RING);
-        S.lag = t == 0 ? 1 : 2; S.nproc = nproc; S.tag = t << 20;
+        S.pred = rq_s32(bars + t * RQ_RING); S.mine = rq_s32(bars + (1 + t) * RQ_RING);
+        S.lag = t == 0 ? 1 : 2; S.nproc = nproc; S.tag = t << 20; S.bar_id = 1 + t;
         S.e_dn = (RQ_NL - 1) * ROW; S.e_own = 0; S.e_up = ROW; S.sl_up = 1; S.ROW = ROW;
-        S.i0r = i0c - e0; S.i1r = i1c - e0;
+        S.i0r = own0; S.i1r = i1c - e0;
         S.skip = (P.xflags & 1) != 0;
         S.mymax = 0.0f;
         if ((colour + e0) & 1) rq_pair_stage<1, STATS>(S); else rq_pair_stage<0, STATS>(S);
-        float mymax = S.mymax;
         if (STATS) {
-            mymax = warp_max(mymax);
+            const float mymax = warp_max(S.mymax);
             if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 >> 1) + t), __float_as_uint(mymax));
         }
-    } else if (warp < RQ_SW + 4) {
-#else
-    if (warp < 16) {
-        // ================= half sweep `warp` =================
-        const int s = warp;
-        if (s >= nst) return;
-        const int colour = (P.stage0 + s) & 1;
-        const float wd = P.wd[s];
-        const float c4 = wd * 0.25f;
-        const float *tw = tblw + 8 * s;
-        const int NDO = RQ_NL * WL, lane4 = 4 * lane;
-        float mymax = 0.0f;
-        int a = (colour + e0) & 1;
-        // slots of lines rel-1, rel, rel+1 (element offsets), rotated line by line
-        int e_dn = (RQ_NL - 1) * ROW, e_own = 0, e_up = ROW, sl_up = 1;
-        // hand-off barriers: wait on the predecessor's (role s) barrier of line rel+1, arrive on ours (role 1+s) of line rel
-        const unsigned wbase = rq_s32(bars + s * RQ_RING), abase = rq_s32(bars + (1 + s) * RQ_RING);
-        const int rlo = 1 - e0, rhi = NX - 2 - e0;   // lines with updatable cells: rel in [rlo, rhi]
-        const bool skip = (P.xflags & 1) != 0;
-        RQCarry cy;
-        bool have = false;
-        for (int rel = 0; rel < nproc; rel++) {
-            const int w = rel + 1;
-            rq_mbar_wait_a(wbase + 8u * (unsigned)(w & (RQ_RING - 1)), (unsigned)(w >> 6) & 1u, (s << 20) | w);
-            if (rel >= rlo && rel <= rhi && !skip) {
-                const int r = e0 + rel;
-                const bool row_owned = (r >= i0c) && (r < i1c);
-                if (a) rq_line<1, STATS>(sQ, sC, e_own, e_up, e_dn, WQ, NDO, lane4, wd, c4, row_owned, P.TJ, mymax, tw, cy, have);
-                else   rq_line<0, STATS>(sQ, sC, e_own, e_up, e_dn, WQ, NDO, lane4, wd, c4, row_owned, P.TJ, mymax, tw, cy, have);
-                have = true;
-            } else {
-                have = false;
-            }
-            rq_arrive_a(abase + 8u * (unsigned)(rel & (RQ_RING - 1)));
-            e_dn = e_own; e_own = e_up;
-            if (++sl_up == RQ_NL) { sl_up = 0; e_up = 0; } else e_up += ROW;
-            a ^= 1;
-        }
-        rq_arrive_a(abase + 8u * (unsigned)(nproc & (RQ_RING - 1)));   // line e1 is never swept: lets the next half sweep finish its last line
-        if (STATS) {
-            mymax = warp_max(mymax);
-            if (lane == 0 && mymax > 0.0f) atomicMax(P.stats + ((P.stage0 + s) >> 1), __float_as_uint(mymax));
-        }
-    } else if (warp < 20) {
-#endif
+    } else if (warp < RQ_SW + RQ_LW) {
         // ================= loader: staging -> slot, lines e0 .. e1 =================
-        const int ld = tid - RQ_LD0;
-        const bool active = ld < (WL >> 2);
-        const int j = jr0 + 4 * ld;
-        const bool col_in = active && j >= 0 && j < PIT;
-        const bool v4_in = j + 4 < PIT;
-        if (active) {   // the slot "below" line e0 (relative -1) must read as q = 0
-            const int q = 2 * ld, b0 = (RQ_NL - 1) * ROW + q;
-            *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
-            *reinterpret_cast<float2 *>(sQ + b0 + WQ) = make_float2(0.f, 0.f);
-        }
-        const int last_owned = (i1c - 1) - e0;
+        // Loader warp k takes lines k, k + RQ_LW, ...: a lane owns 4 columns in each of the 4 groups of 128, so a
+        // warp has RQ_LW line periods for its line and the groups are independent work.
+        const int lw = warp - RQ_SW;
         // only interior lines inside this rank's slab hold updatable cells (the mask's count bits are
         // zero on the ring and in solids); line e1 is loaded but never swept
         const int live_lo = max(1, g.i_alloc0) - e0;
         const int live_hi = min(min(NX - 2, g.i_alloc0 + g.lines_alloc - 2), e1 - 1) - e0;
-        const unsigned b_self = rq_s32(bars), b_writer = rq_s32(bars + RQ_WROLE * RQ_RING), b_last = rq_s32(bars + RQ_LAST_ROLE(nst) * RQ_RING);
-        const unsigned b_full = rq_s32(full);
-        // element offset of this thread's cells in slot 0; staging offsets of lines rel and rel+1
-        int e_row = 2 * ld, sl = 0;
-        int st0 = 0, st1 = (RQ_STG > 1) ? 1 : 0;
-        unsigned par1 = 0;                                   // phase parity of staging slot st1's current use
-        rq_mbar_wait_io(b_full, 0u, (30 << 20));              // line 0 has landed
-        for (int rel = 0; rel <= nproc; rel++) {
-            // slot(rel) last held line y-1 with y = rel-NL+1; its last readers work on line y: the writer
-            // if y is an owned line, otherwise the last half sweep
+        const unsigned b_full = rq_s32(full), ring_last = rq_s32(bars + nit * RQ_RING);
+        int sl = lw;                                         // slot of line rel
+        for (int rel = lw; rel <= nproc; rel += RQ_LW) {
+            // slot(rel) last held line y-1 with y = rel - NL + 1.  Its readers: the stages up to the last one's step y
+            // (which writes line y-1 for the last time) and, for owned lines, the writer at lines y-1 and y.
             const int y = rel - RQ_NL + 1;
             if (y >= 0) {
-                const unsigned bb = (y >= RQ_H && y <= last_owned) ? b_writer : b_last;
-                rq_mbar_wait_io(bb + 8u * (unsigned)(y & (RQ_RING - 1)), (unsigned)(y >> 6) & 1u, (RQ_WROLE << 20) | y);
+                if (y - 1 >= own0 && y - 1 <= last_owned) rq_wait_line(ring_wr, y - 1, 40 << 20);
+                if (y >= own0 && y <= last_owned) rq_wait_line(ring_wr, y, 41 << 20);
+                else rq_wait_line(ring_last, y, 42 << 20);
             }
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            unsigned code = 0;
-            // line rel+1 must have landed too (the producer stages every line 0 .. nproc); line rel was
-            // waited for one iteration ago
-            if (rel < nproc) rq_mbar_wait_io(b_full + 8u * (unsigned)st1, par1, (31 << 20) | rel);
-            if (rel >= live_lo && rel <= live_hi && col_in) {
-                const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
-                const float *stU = reinterpret_cast<const float *>(s0) + 4 * ld, *stV = stU + WL;
-                const float4 u0 = *reinterpret_cast<const float4 *>(stU);
-                const float4 u1 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(s1) + 4 * ld);
-                const float4 v = *reinterpret_cast<const float4 *>(stV);
-                const float v4 = v4_in ? stV[4] : 0.0f;
-                const unsigned mk = *reinterpret_cast<const unsigned *>(s0 + (size_t)(2 * WL + 4) * 4 + 4 * ld);
-                code = (mk >> MK_CNT_SHIFT) & 0x07070707u;   // fluid neighbours of updatable cells, else 0
-                const float dv0 = ((u1.x - u0.x) + v.y) - v.x, dv1 = ((u1.y - u0.y) + v.z) - v.y;
-                const float dv2 = ((u1.z - u0.z) + v.w) - v.z, dv3 = ((u1.w - u0.w) + v4) - v.w;
-                d[0] = (code & 0x000000ffu) ? -dv0 : 0.0f;
-                d[1] = (code & 0x0000ff00u) ? -dv1 : 0.0f;
-                d[2] = (code & 0x00ff0000u) ? -dv2 : 0.0f;
-                d[3] = (code & 0xff000000u) ? -dv3 : 0.0f;
-            }
-            if (active) {
-                const int b0 = e_row, b1 = e_row + WQ;
+            // lines rel and rel+1 have landed (the producer stages every line 0 .. nproc)
+            const int st0 = rel & (RQ_STG - 1), st1 = (rel + 1) & (RQ_STG - 1);
+            rq_wait_a(b_full + 8u * (unsigned)st0, (unsigned)(rel / RQ_STG) & 1u, (30 << 20) | rel);
+            if (rel < nproc) rq_wait_a(b_full + 8u * (unsigned)st1, (unsigned)((rel + 1) / RQ_STG) & 1u, (31 << 20) | rel);
+            const bool live = rel >= live_lo && rel <= live_hi;
+            const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
+            const int e_slot = sl * ROW;
+#pragma unroll
+            for (int cg = 0; cg < 4; cg++) {
+                const int ld = lane + 32 * cg;
+                const int j = jr0 + 4 * ld;
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                unsigned code = 0;
+                if (live && j >= 0 && j < PIT && !(P.xflags & 8)) {
+                    const float *stU = reinterpret_cast<const float *>(s0) + 4 * ld, *stV = stU + WL;
+                    const float4 u0 = *reinterpret_cast<const float4 *>(stU);
+                    const float4 u1 = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(s1) + 4 * ld);
+                    const float4 v = *reinterpret_cast<const float4 *>(stV);
+                    const float v4 = (j + 4 < PIT) ? stV[4] : 0.0f;
+                    const unsigned mk = *reinterpret_cast<const unsigned *>(s0 + (size_t)(2 * WL + 4) * 4 + 4 * ld);
+                    code = (mk >> MK_CNT_SHIFT) & 0x07070707u;   // fluid neighbours of updatable cells, else 0
+                    const float dv0 = ((u1.x - u0.x) + v.y) - v.x, dv1 = ((u1.y - u0.y) + v.z) - v.y;
+                    const float dv2 = ((u1.z - u0.z) + v.w) - v.z, dv3 = ((u1.w - u0.w) + v4) - v.w;
+                    d[0] = (code & 0x000000ffu) ? -dv0 : 0.0f;
+                    d[1] = (code & 0x0000ff00u) ? -dv1 : 0.0f;
+                    d[2] = (code & 0x00ff0000u) ? -dv2 : 0.0f;
+                    d[3] = (code & 0xff000000u) ? -dv3 : 0.0f;
+                }
+                const int b0 = e_slot + 2 * ld, b1 = b0 + WQ;
+                if (P.xflags & 16) continue;
                 *reinterpret_cast<float2 *>(sND + b0) = make_float2(d[0], d[2]);
                 *reinterpret_cast<float2 *>(sND + b1) = make_float2(d[1], d[3]);
                 *reinterpret_cast<float2 *>(sQ + b0) = make_float2(0.f, 0.f);
@@ -638,47 +472,40 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 *reinterpret_cast<unsigned short *>(sC + b0) = (unsigned short)__byte_perm(code, 0u, 0x4420);
                 *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)__byte_perm(code, 0u, 0x4431);
             }
-            rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));
-            if (++sl == RQ_NL) { sl = 0; e_row = 2 * ld; } else e_row += ROW;
-            st0 = st1;
-            if (++st1 == RQ_STG) { st1 = 0; par1 ^= 1u; }
+            rq_done_line(ring_ld, rel);
+            sl += RQ_LW; if (sl >= RQ_NL) sl -= RQ_NL;
         }
-    } else if (warp < RQ_SW + 8) {
+    } else if (warp < RQ_SW + RQ_LW + RQ_WW) {
         // ================= writer: owned lines -> U, V, p =================
-        // U0, V0 and the mask of the line come from the writer's own TMA staging ring (second
-        // producer below).  They were fetched through registers before: the re-read misses L2 more
-        // often than not (ncu: 35 % read hit rate) and the register ring did not survive code
-        // generation, so every line paid a DRAM round trip (74 % of the writer's stall samples).
-        const int st = tid - RQ_WR0;
-        const bool active = st < (P.TJ >> 2);
-        const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
-        const bool col_ok = active && w_j < NY && !(P.xflags & 2);
-        const bool full4 = w_j + 3 < NY;
-        const unsigned b_self = rq_s32(bars + RQ_WROLE * RQ_RING), b_last = rq_s32(bars + RQ_LAST_ROLE(nst) * RQ_RING), b_wfull = rq_s32(wfull);
+        // Writer warp k takes the owned lines i0c + k, i0c + k + RQ_WW, ... (all their columns).  U0, V0 and the
+        // mask of a line come from the writer's own TMA staging ring (second producer below): re-read through
+        // registers they missed L2 two times in three and every line paid a DRAM round trip.
+        const int ww = warp - RQ_SW - RQ_LW;
+        const unsigned b_wfull = rq_s32(wfull), ring_last = rq_s32(bars + nit * RQ_RING);
         // only owned lines are written, but the hand-off phases count every line: arrive for the halo lines first
-        for (int rel = 0; rel < i0c - e0; rel++) rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));
-        int sl = (i0c - e0) % RQ_NL;
-        // this thread's cells: q index in a slot, staging offsets, global offset of line i0c
-        const int q = w_lj >> 1;
-        int e_row = sl * ROW + q, e_rowm = (sl == 0 ? RQ_NL - 1 : sl - 1) * ROW + q;
-        int ws = 0;
-        unsigned wpar = 0;
-        const unsigned char *sb = wstg + 16 * st;
-        const int oV = 4 * P.TJ, oM = 8 * P.TJ - 12 * st;    // byte offsets of V and the mask word from sb
-        size_t o = (size_t)(i0c - g.i_alloc0) * PIT + w_j;
+        for (int rel = ww; rel < own0; rel += RQ_WW) rq_done_line(ring_wr, rel);
+        int sl = (own0 + ww) % RQ_NL;
         const bool turb = P.turb > 0.0f;
         const float cp = P.cp;
-        for (int r = i0c; r < i1c; r++) {
-            const int rel = r - e0;
-            {   // the last half sweep is past line r (RQ_PAIR: the last iteration has finished its step rel+1)
-                const int wl = rel + RQ_PAIR;
-                rq_mbar_wait_io(b_last + 8u * (unsigned)(wl & (RQ_RING - 1)), (unsigned)(wl >> 6) & 1u, (nst << 20) | rel);
-            }
-            rq_mbar_wait_io(b_wfull + 8u * (unsigned)ws, wpar, (32 << 20) | rel);     // U0, V0, mask of line r have landed
-            if (col_ok) {
+        const int oV = 4 * P.TJ;
+        for (int n = ww; n < i1c - i0c; n += RQ_WW) {
+            const int r = i0c + n, rel = r - e0;
+            rq_wait_line(ring_last, rel + 1, nst << 20);                // the last iteration has finished its step rel+1: line r is final
+            const int ws = n & (RQ_WSTG - 1);
+            rq_wait_a(b_wfull + 8u * (unsigned)ws, (unsigned)(n / RQ_WSTG) & 1u, (32 << 20) | rel);   // U0, V0, mask of line r have landed
+            const int e_line = sl * ROW, e_linem = (sl == 0 ? RQ_NL - 1 : sl - 1) * ROW;
+            const bool line_first = (r == 0);
+#pragma unroll 2
+            for (int cg = 0; cg < 4; cg++) {
+                const int st = lane + 32 * cg;
+                const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
+                if (st >= (P.TJ >> 2) || w_j >= NY || (P.xflags & 2)) continue;
+                const int q = w_lj >> 1, e_row = e_line + q, e_rowm = e_linem + q;
+                const unsigned char *sb = wstg + ws * WSTGB + 16 * st;
+                const size_t o = (size_t)(r - g.i_alloc0) * PIT + w_j;
                 const float4 u = *reinterpret_cast<const float4 *>(sb);
                 const float4 v = *reinterpret_cast<const float4 *>(sb + oV);
-                const unsigned m4 = *reinterpret_cast<const unsigned *>(sb + oM);
+                const unsigned m4 = *reinterpret_cast<const unsigned *>(sb + 2 * oV - 12 * st);
                 float pin[4] = {0.f, 0.f, 0.f, 0.f};
                 if (P.Pin) unpack(ld4(P.Pin + o), pin);
                 const float2 ev = *reinterpret_cast<const float2 *>(sQ + e_row);
@@ -688,7 +515,6 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 const float ql = sQ[e_row + WQ - 1];                   // column lj-1 (odd parity, index q-1)
                 const float qc[4] = { ev.x, od.x, ev.y, od.y }, qx[4] = { evm.x, odm.x, evm.y, odm.y };
                 const float uu[4] = { u.x, u.y, u.z, u.w }, vv[4] = { v.x, v.y, v.z, v.w };
-                const bool line_first = (r == 0);
                 float pu[4], pv[4], pp[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -723,7 +549,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                         }
                     }
                 }
-                if (full4) {
+                if (w_j + 3 < NY) {
                     *reinterpret_cast<float4 *>(P.Uo + o) = make_float4(pu[0], pu[1], pu[2], pu[3]);
                     *reinterpret_cast<float4 *>(P.Vo + o) = make_float4(pv[0], pv[1], pv[2], pv[3]);
                     *reinterpret_cast<float4 *>(P.Po + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
@@ -731,11 +557,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                     for (int k = 0; k < 4 && w_j + k < NY; k++) { P.Uo[o + k] = pu[k]; P.Vo[o + k] = pv[k]; P.Po[o + k] = pp[k]; }
                 }
             }
-            rq_arrive_a(b_self + 8u * (unsigned)(rel & (RQ_RING - 1)));       // slots and staging of line r are free
-            e_rowm = e_row;
-            if (++sl == RQ_NL) { sl = 0; e_row = q; } else e_row += ROW;
-            if (++ws == RQ_WSTG) { ws = 0; wpar ^= 1u; sb = wstg + 16 * st; } else sb += WSTGB;
-            o += PIT;
+            rq_done_line(ring_wr, rel);                               // slots and staging of line r are free
+            sl += RQ_WW; if (sl >= RQ_NL) sl -= RQ_NL;
         }
     } else if (tid == RQ_P2) {
         // ================= second producer: U0, V0, mask of the owned lines for the writer =================
@@ -747,15 +570,16 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const float *gU = P.U + o0, *gV = P.V + o0;
         const unsigned char *gM = P.mask + o0;
         int ws = 0;
-        for (int r = i0c; r < i1c; r++) {
-            if (r - i0c >= RQ_WSTG) rq_wait_line(bars, RQ_WROLE, r - RQ_WSTG - e0);   // the writer is done with this stage
-            unsigned char *sb = wstg + ws * WSTGB;
+        for (int n = 0; n < i1c - i0c; n++) {
+            // the writer warp that had this staging slot (line n - RQ_WSTG) is done with it
+            if (n >= RQ_WSTG) rq_wait_line(ring_wr, own0 + n - RQ_WSTG, 33 << 20);
+            const unsigned sb = rq_s32(wstg + ws * WSTGB), fb = rq_s32(wfull + ws);
             if (!skip) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 rq_mbar_expect_tx(wfull + ws, bytes);
-                rq_tma_load(sb, gU, bF, wfull + ws);
-                rq_tma_load(sb + 4 * P.TJ, gV, bF, wfull + ws);
-                rq_tma_load(sb + 8 * P.TJ, gM, bM, wfull + ws);
+                rq_tma_load(sb, gU, bF, fb);
+                rq_tma_load(sb + 4 * P.TJ, gV, bF, fb);
+                rq_tma_load(sb + 8 * P.TJ, gM, bM, fb);
             } else {
                 rq_mbar_arrive(wfull + ws);
             }
@@ -764,9 +588,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         }
     } else if (tid == RQ_P1) {
         // ================= producer: TMA bulk copies into the staging ring =================
-        // line rel goes to staging slot rel % RQ_STG once the loader is past line rel - RQ_STG
-        // (the loader reads staging slot(rel) for lines rel-1 and rel).  One thread: everything
-        // that does not change from line to line is hoisted, the loop body is ~30 instructions.
+        // line rel goes to staging slot rel % RQ_STG once the loader is past lines rel - RQ_STG and
+        // rel - RQ_STG - 1 (the loader reads staging slot(rel) for lines rel-1 and rel; this loop has
+        // waited for the earlier line one trip ago).
         const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
         const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
         const int off = cj0 - jr0;                                            // staging column of global column cj0
@@ -775,43 +599,27 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         // lines that exist in this rank's planes: relative [relA, relB)
         const int lineA = max(0, g.i_alloc0), lineB = min(NX, g.i_alloc0 + g.lines_alloc);
         const int relA = lineA - e0, relB = (cjU > cj0 && !(P.xflags & 4)) ? lineB - e0 : -1;
-        unsigned dU[RQ_STG], dV[RQ_STG], dM[RQ_STG], fb[RQ_STG];
-#pragma unroll
-        for (int k = 0; k < RQ_STG; k++) {
-            unsigned char *s0 = stg + k * STG;
-            dU[k] = rq_s32(reinterpret_cast<float *>(s0) + off);
-            dV[k] = rq_s32(reinterpret_cast<float *>(s0) + WL + off);
-            dM[k] = rq_s32(s0 + (size_t)(2 * WL + 4) * 4 + off);
-            fb[k] = rq_s32(full + k);
-        }
         const long long o0 = (long long)(e0 - g.i_alloc0) * PIT + cj0;       // offset of relative line 0 (may be negative)
         const float *gU = P.U + o0, *gV = P.V + o0;
         const unsigned char *gM = P.mask + o0;
-        const unsigned lbase = rq_s32(bars);                                  // loader hand-off barriers (role 0)
-        for (int rel0 = 0; rel0 <= nproc; rel0 += RQ_STG) {
-#pragma unroll
-            for (int k = 0; k < RQ_STG; k++) {
-                const int rel = rel0 + k;
-                if (rel > nproc) break;
-                if (rel >= RQ_STG) {
-                    const int w = rel - RQ_STG;
-                    rq_mbar_wait_io(lbase + 8u * (unsigned)(w & (RQ_RING - 1)), (unsigned)(w / RQ_RING) & 1u, w);
-                }
-                if (rel >= relA && rel < relB) {
-                    // order prior generic-proxy reads of this staging slot before the async-proxy writes
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb[k]), "r"(bytes) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dU[k]), "l"(gU), "r"(bU), "r"(fb[k]) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dV[k]), "l"(gV), "r"(bV), "r"(fb[k]) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dM[k]), "l"(gM), "r"(bM), "r"(fb[k]) : "memory");
-                } else {
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb[k]) : "memory");
-                }
-                gU += PIT; gV += PIT; gM += PIT;
+        for (int rel = 0; rel <= nproc; rel++) {
+            const int k = rel & (RQ_STG - 1);
+            if (rel >= RQ_STG) {
+                rq_wait_line(ring_ld, rel - RQ_STG, 34 << 20);
             }
+            unsigned char *s0 = stg + k * STG;
+            const unsigned fb = rq_s32(full + k);
+            if (rel >= relA && rel < relB) {
+                // order prior generic-proxy reads of this staging slot before the async-proxy writes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                rq_mbar_expect_tx(full + k, bytes);
+                rq_tma_load(rq_s32(reinterpret_cast<float *>(s0) + off), gU, bU, fb);
+                rq_tma_load(rq_s32(reinterpret_cast<float *>(s0) + WL + off), gV, bV, fb);
+                rq_tma_load(rq_s32(s0 + (size_t)(2 * WL + 4) * 4 + off), gM, bM, fb);
+            } else {
+                rq_mbar_arrive(full + k);
+            }
+            gU += PIT; gV += PIT; gM += PIT;
         }
     }
 }
