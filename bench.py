@@ -49,6 +49,10 @@ WORKLOADS = {
     "cavity1024": ("cavity", 1024, 1024, True, 0.0, "configs[1]: lid-driven cavity 1024^2, BFECC (fits L2)"),
     "jet300": ("jet", 300, 251, False, 0.0, "configs[0]: jet at the reference's default 300x251 grid"),
     "karman1024": ("karman", 1024, 1024, True, 0.1, "Karman 1024^2 (CPU sample size)"),
+    # projection only (fill(p,0) + makeIncompressible, fluid.go:83 + 144-234) on a FIXED grid split over the ranks
+    "project32768": ("projection", 32768, 32768, False, 0.0, "configs[4]: pressure projection on a fixed 32768^2 grid with walls and sources (strong scaling)"),
+    "project8192": ("projection", 8192, 8192, False, 0.0, "configs[4] at 8192^2"),
+    "project4096": ("projection", 4096, 4096, False, 0.0, "configs[4] at 4096^2 (the size the CPU oracle's residual target is computed at)"),
 }
 
 
@@ -168,6 +172,242 @@ def dist_env():
     return rank, world, local
 
 
+def splitmix_uniform_torch(torch, n, seed, start, device):
+    """presets.splitmix_uniform on a torch device (int64 arithmetic wraps like uint64; logical shifts masked)."""
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    def s64(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+    idx = torch.arange(start + 1, start + n + 1, dtype=torch.int64, device=device)
+    z = idx * s64(0x9E3779B97F4A7C15) + s64(seed)
+    z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    u = lsr(z, 40).to(torch.float64) / float(1 << 24)
+    return (u * 2.0 - 1.0).to(torch.float32)
+
+
+def projection_cpu_run(size, solves, warmup=1):
+    """The reference's projection (lexicographic GS/SOR, sequential: one core) on the config-5 input at `size`^2:
+    time per solve and the residual it reaches -- the target the GPU solver is held to."""
+    import oracle
+    from fluid_b200 import presets
+    p = presets.projection_stress(size, size)
+    f = oracle.New(p.density, size, size, p.h, solver=oracle.SOLVER_EXACT)
+    u, v = presets.projection_fields(size + 2, size + 2, 0, size + 2)
+    f.set("U", u); f.set("V", v)
+    f.edit(p.init); f.edit(p.per_step)
+    u0, v0 = f.get("U").copy(), f.get("V").copy()
+    before = float(f.MaxDivergence())
+    f.project(8, p.dt)
+    after = float(f.MaxDivergence())
+    times = []
+    for k in range(warmup + solves):
+        f.set("U", u0); f.set("V", v0)
+        t0 = time.perf_counter()
+        f.project(8, p.dt)
+        if k >= warmup:
+            times.append(time.perf_counter() - t0)
+    cells = (size + 2) * (size + 2)
+    sec = sum(times) / len(times)
+    return {"value": cells / sec, "unit": "cell-steps/s", "cores": 1, "kind": "port", "ms_per_step": sec * 1e3,
+            "sample": f"config-5 input at {size}^2 (+ring): fill(p,0) + makeIncompressible(8) of the oracle/ C restatement, "
+                      f"lexicographic in-place GS/SOR -- sequential in the reference too (fluid.go:188-234), 1 thread; "
+                      f"{solves} solves after {warmup} warm-up",
+            "max_div_before": before, "max_div_after_8_sweeps": after}
+
+
+def run_projection(args, rank, world, local):
+    """configs[4]: projection only, FIXED global grid (strong scaling), row slabs over the ranks.  One "step" is
+    fill(p,0) + makeIncompressible(8) (fluid.go:83, 144-234) over the whole grid, preceded for N > 1 by the
+    exchange of 16 ghost lines of U, V with both neighbours."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import fluid_b200
+    from fluid_b200 import _lib as L
+    from fluid_b200 import parallel, presets
+
+    pname, width, height, _b, _c, cfg_desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        size = min(width, 4096)
+        r = projection_cpu_run(size, max(min(args.steps, 5), 1), 1)
+        line = {"impl": "reference", "metric": "cell-steps/s", "value": r["value"], "unit": "cell-steps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "restates": cfg_desc, "step": "one projection (8 sweeps)",
+                           "solver": "lexicographic (reference)", "sample_grid": [size + 2, size + 2]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    solver = {"pressure": fluid_b200.SOLVER_REDBLACK_PRESSURE, "redblack": fluid_b200.SOLVER_REDBLACK,
+              "exact": fluid_b200.SOLVER_EXACT}[args.solver]
+    preset = presets.projection_stress(width, height)
+    ghost = 32 if world > 1 else 0
+    if world > 1:
+        sim = parallel.SlabFluid(preset.density, width, height, preset.h, solver=solver, device=local, rank=rank,
+                                 nranks=world, ghost=ghost, reach=1, transport=args.transport)
+        f = sim.f
+    else:
+        sim = f = fluid_b200.New(preset.density, width, height, preset.h, solver=solver, device=local)
+    NX, NY = f.NumX, f.NumY
+    a0 = max(0, f.i_lo - ghost)
+    lines = min(NX, f.i_hi + ghost) - a0
+    # the rank's lines of the SplitMix64 field (U = values 0 .. NX*NY-1 of the stream, V the next NX*NY), generated on
+    # the device and parked in pinned host memory: the end-to-end leg uploads them every step
+    host = {}
+    for name, base in (("U", 0), ("V", NX * NY)):
+        buf = torch.empty((lines, NY), dtype=torch.float32, pin_memory=True)
+        for l0 in range(0, lines, 2048):
+            l1 = min(l0 + 2048, lines)
+            buf[l0:l1].copy_(splitmix_uniform_torch(torch, (l1 - l0) * NY, 0x5EED, base + (a0 + l0) * NY, dev).view(l1 - l0, NY))
+        host[name] = buf
+    torch.cuda.synchronize()
+
+    def upload():
+        # fb_upload addresses a GLOBAL [NumX][NumY] array and copies the lines this rank holds: pass the window's origin
+        for name in ("U", "V"):
+            L.check(f._h, L.lib.fb_upload(f._h, L.FIELD_NAMES[name], C.c_void_p(host[name].data_ptr() - a0 * NY * 4)))
+
+    upload()
+    sim.edit(preset.init)        # all fluid, 8x8 obstacle lattice, four walls: SetSolid zeroes the faces of solid cells (Q-16)
+    sim.edit(preset.per_step)    # the +-5 sources on three rows
+    # keep the PREPARED field in the pinned buffers (faces zeroed, sources set)
+    for name in ("U", "V"):
+        L.check(f._h, L.lib.fb_download(f._h, L.FIELD_NAMES[name], C.c_void_p(host[name].data_ptr() - a0 * NY * 4)))
+    if world > 1:
+        upload()                 # fb_download fills owned lines only; ghosts come from the exchange below
+
+    def solve():
+        sim.project(8, preset.dt)      # N > 1: SlabFluid.project refreshes the ghost lines first
+
+    div_before = sim.MaxDivergence()
+    residuals = {}
+    done = 0
+    for target in (1, 2, 4, 8):
+        while done < target:
+            solve(); done += 1
+        residuals[str(8 * target)] = sim.MaxDivergence()
+    for _ in range(max(args.warmup - 8, 0)):
+        solve()
+    f.set_option(L.OPT_SOLVE_STATS, 0)
+    f.profile(True); f.profile_read()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = f.launch_count()
+    barrier()
+    f.timer_start()
+    for _ in range(args.steps):
+        solve()
+    ms = f.timer_stop()
+    barrier()
+    ms = allmax(ms)
+    launches = f.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else {}
+    phases = f.profile_read()
+    f.profile(False)
+    cells_total = NX * NY
+    value = cells_total * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    proj_ms = allmax(phases["project"][0] / max(phases["project"][1], 1))
+    cells_rank = (f.i_hi - f.i_lo) * NY
+    achieved = 24 * cells_rank / (proj_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            traffic = json.load(fh).get(args.workload, {}).get("project")
+    except Exception:
+        traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_rbq_fused" if args.solver == "pressure" else "k_rb_fused", "phase": "project",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "alg_bytes_per_cell": 24.0, "ms_per_launch": proj_ms,
+                "share_of_step": proj_ms / (ms / args.steps),
+                "pressure_solve": {"alg_bytes_per_cell": 24, "ms": proj_ms, "achieved": achieved, "frac": achieved / peak,
+                                   "aggregate_GBps": 24 * cells_total / (ms / args.steps * 1e-3) / 1e9},
+                "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1] > 0}}
+
+    # ---- e2e: the same projection through the C ABI with HOST buffers: per step the rank's lines of U and V go
+    # host -> device from pinned memory, the halo exchange and the solve run, and the step's result (max |div|) comes back
+    e2e = None
+    if not args.no_secondary:
+        n_e2e = max(1, min(args.steps, 3))
+        def e2e_step():
+            upload()
+            solve()
+            return sim.MaxDivergence()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = allmax(time.perf_counter() - t0)
+        e2e = {"value": cells_total * n_e2e / e2e_s, "unit": "cell-steps/s", "steps": n_e2e,
+               "h2d_bytes_per_step": int(2 * lines * NY * 4) * world, "d2h_bytes_per_step": 4 * world,
+               "ms_per_step": e2e_s / n_e2e * 1e3,
+               "what": "per step and rank: fb_upload of U and V (the lines the rank holds) from pinned host memory, halo "
+                       "exchange, fill(p,0) + makeIncompressible(8), MaxDivergence() read back"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        r = projection_cpu_run(min(width, 4096), 3, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "max_div_before", "max_div_after_8_sweeps")}
+    if world > 1:
+        sim.check_halo()
+    if rank == 0:
+        line = {
+            "metric": "cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "restates": cfg_desc, "step": "one projection: fill(p,0) + makeIncompressible(8 iterations)",
+                       "grid_total": [NX, NY], "cells_total": cells_total, "grid_per_gpu": [f.i_hi - f.i_lo, NY],
+                       "input": "U, V = float32 uniform(-1,1) from SplitMix64(0x5EED) in linear-index order; four walls, 8x8 lattice of "
+                                "circular obstacles of radius H/64, +-5 sources every 64th cell on three rows (SURVEY.md 8d)",
+                       "parallelism": "single GPU" if world == 1 else
+                                      f"row slabs over i, {world} ranks, {ghost} ghost lines of U, V refreshed before every solve "
+                                      f"({'peer memory over NVLink' if args.transport == 'peer' else 'NCCL send/recv'})",
+                       "solver": {"pressure": "red-black SOR in pressure form, 8 iterations fused in one pass",
+                                  "redblack": "red-black SOR on the face velocities, 8 iterations fused",
+                                  "exact": "lexicographic GS/SOR (wavefront), 8 sweeps"}[args.solver],
+                       "l2": "working set >> 126 MB L2 (inputs larger than L2)" if cells_rank > 8e6 else "working set fits L2",
+                       "residual": {"max_div_before": div_before, "max_div_after_iterations": residuals,
+                                    "note": "target = the reference's (lexicographic) max|div| after its 8 sweeps on the same "
+                                            "input, cpu_baseline.max_div_after_8_sweeps, computed at min(size, 4096)^2"}},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +424,8 @@ def main():
 
     rank, world, local = dist_env()
     pname, width, height, bfecc, conf, cfg_desc = WORKLOADS[args.workload]
+    if pname == "projection":
+        return run_projection(args, rank, world, local)
     bpc = step_bytes(bfecc, conf)
 
     if args.impl == "reference":

@@ -25,7 +25,7 @@ FLAG_LITERAL, FLAG_EXACT_SHADOW = 1, 2
 # fb_phase_id
 (PHASE_MAKE_INCOMPRESSIBLE, PHASE_ADVECT_VELOCITY, PHASE_ADVECT_SMOKE, PHASE_HANDLE_BORDERS, PHASE_CONFINEMENT,
  PHASE_TURBULENCE, PHASE_ADVECT_VELOCITY_BFECC, PHASE_ADVECT_SMOKE_BFECC, PHASE_VISCOSITY,
- PHASE_CLEAR_PRESSURE) = range(10)
+ PHASE_CLEAR_PRESSURE, PHASE_PROJECT) = range(11)
 # fb_view_kind / fb_reduce_kind
 VIEW_SMOKE, VIEW_PRESSURE, VIEW_VELOCITY_MAGNITUDE, VIEW_VORTICITY = range(4)
 REDUCE_MAX_DIVERGENCE, REDUCE_MAX_ABS_VELOCITY = range(2)

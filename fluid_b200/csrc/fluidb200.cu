@@ -1378,6 +1378,12 @@ extern "C" int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float d
     case FB_PHASE_ADVECT_SMOKE_BFECC: return h->literal ? advect_smoke_bfecc(h, p, dt) : advect_smoke_bfecc_fast(h, p, dt);
     case FB_PHASE_VISCOSITY: return apply_viscosity(h, p, dt);
     case FB_PHASE_CLEAR_PRESSURE: return clear_pressure(h);
+    case FB_PHASE_PROJECT: {
+        ProfScope ps(h, FB_PROF_PROJECT);
+        if (h->literal || p->solver == FB_SOLVER_EXACT || iters == 0) TRY(clear_pressure(h));
+        else h->p_zero = true;                         // the fused red-black solvers never read a zero pressure
+        return make_incompressible(h, p, dt, iters);
+    }
     default: return fail(h, FB_ERR_INVALID, "unknown phase");
     }
 }

@@ -289,12 +289,17 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
                 qo[half] = *reinterpret_cast<const float4 *>(sQ + own + h0);
                 up[half] = *reinterpret_cast<const float4 *>(sQ + upo + h0);
                 nd[half] = *reinterpret_cast<const float4 *>(sQ + own + h0 + S.NDO);
-                ox[half] = sQ[oth + h0 + (A ? 4 : -1)];
+                // left / right neighbour beyond this lane's four cells: the next / previous lane holds it in a register
+                // (a scalar LDS at a 16-byte stride is a 4-way bank conflict); only the lane at the end of the
+                // warp's group reads shared memory (the other warp's cell, or the halo column)
+                ox[half] = A ? __shfl_down_sync(0xffffffffu, P1[half].x, 1) : __shfl_up_sync(0xffffffffu, P1[half].w, 1);
+                if (S.lane == (A ? 31 : 0)) ox[half] = sQ[oth + h0 + (A ? 4 : -1)];
                 code[half] = *reinterpret_cast<const unsigned *>(S.sC + own + h0);
             }
             if (SECOND) {
                 nd2[half] = *reinterpret_cast<const float4 *>(sQ + own2 + h0 + S.NDO);
-                ox2[half] = sQ[oth2 + h0];
+                ox2[half] = A ? __shfl_down_sync(0xffffffffu, F1[half].x, 1) : __shfl_up_sync(0xffffffffu, F1[half].w, 1);
+                if (S.lane == (A ? 31 : 0)) ox2[half] = sQ[oth2 + h0];
                 code2[half] = *reinterpret_cast<const unsigned *>(S.sC + own2 + h0);
             }
         }

@@ -259,6 +259,9 @@ class Fluid:
     def clearPressure(self):                                  # fluid.go:83
         self._phase(L.PHASE_CLEAR_PRESSURE)
 
+    def project(self, numIters: int, dt: float):              # fluid.go:83 + 90, as Simulate runs them
+        self._phase(L.PHASE_PROJECT, dt, numIters)
+
     def solve_stats(self):
         st = L.SolveStats()
         L.check(self._h, L.lib.fb_get_solve_stats(self._h, C.byref(st)))

@@ -230,6 +230,14 @@ class SlabFluid:
         if self._steps_since_check >= 16:
             self.check_halo()
 
+    def project(self, numIters, dt):
+        """fill(p,0) + makeIncompressible(numIters) on the slab, after refreshing the ghost lines of U, V
+        (one pass of <= 8 iterations reads 16 of them; BASELINE config 5)."""
+        if numIters > 8 and self.nranks > 1:
+            raise ValueError("a slab solve is one pass of at most 8 iterations between halo exchanges")
+        self.exchange()
+        self.f.project(numIters, dt)
+
     def check_halo(self):
         self._steps_since_check = 0
         L.check(self.f._h, L.lib.fb_check_halo(self.f._h))
@@ -320,6 +328,11 @@ class LocalSlabGroup:
                 s.step_no_exchange(dt, arr)
         for s in self.slabs:
             s.check_halo()
+
+    def project(self, numIters, dt):
+        exchange_local(self.slabs)
+        for s in self.slabs:
+            s.f.project(numIters, dt)
 
     def get(self, name):
         out = np.zeros((self.NumX, self.NumY), dtype=np.float32)

@@ -110,9 +110,11 @@ def projection_stress(width: int, height: int, seed: int = 0x5EED):
     return Preset("projection", width, height, E.pack(init), E.pack(src), {})
 
 
-def splitmix_uniform(n: int, seed: int) -> np.ndarray:
-    """float32 uniform(-1,1) from SplitMix64, consumed in index order."""
-    idx = np.arange(1, n + 1, dtype=np.uint64)
+def splitmix_uniform(n: int, seed: int, start: int = 0) -> np.ndarray:
+    """float32 uniform(-1,1) from SplitMix64, consumed in index order: values ``start .. start+n-1``
+    of the stream (value k comes from state ``seed + (k+1)*gamma``, so any window can be generated
+    on its own -- a rank fills only the lines it holds)."""
+    idx = np.arange(start + 1, start + n + 1, dtype=np.uint64)
     with np.errstate(over="ignore"):
         z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
@@ -120,6 +122,20 @@ def splitmix_uniform(n: int, seed: int) -> np.ndarray:
         z = z ^ (z >> np.uint64(31))
     u = (z >> np.uint64(40)).astype(np.float64) / float(1 << 24)
     return (u * 2.0 - 1.0).astype(np.float32)
+
+
+def projection_fields(num_x: int, num_y: int, line0: int, nlines: int, seed: int = 0x5EED, chunk_lines: int = 256):
+    """Config 5's pre-projection velocity field for lines ``line0 .. line0+nlines-1``:
+    U takes the first NumX*NumY values of the stream in linear-index order, V the next NumX*NumY."""
+    n = num_x * num_y
+    out = []
+    for base in (0, n):
+        a = np.empty((nlines, num_y), dtype=np.float32)
+        for l0 in range(0, nlines, chunk_lines):
+            l1 = min(l0 + chunk_lines, nlines)
+            a[l0:l1] = splitmix_uniform((l1 - l0) * num_y, seed, base + (line0 + l0) * num_y).reshape(l1 - l0, num_y)
+        out.append(a)
+    return out[0], out[1]
 
 
 BY_NAME = {"jet": jet, "cavity": cavity, "karman": karman}

@@ -130,7 +130,9 @@ typedef enum fb_phase_id {
     FB_PHASE_ADVECT_VELOCITY_BFECC = 6,/* fluid.go:911 */
     FB_PHASE_ADVECT_SMOKE_BFECC = 7,   /* fluid.go:997 */
     FB_PHASE_VISCOSITY = 8,            /* fluid.go:112 */
-    FB_PHASE_CLEAR_PRESSURE = 9        /* fluid.go:83 */
+    FB_PHASE_CLEAR_PRESSURE = 9,       /* fluid.go:83 */
+    FB_PHASE_PROJECT = 10              /* fluid.go:83 + 90 as Simulate runs them: fill(p,0) then makeIncompressible(iters);
+                                        * the fused solvers write p without reading it, so the fill costs no pass over HBM */
 } fb_phase_id;
 
 typedef enum fb_view_kind {

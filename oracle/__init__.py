@@ -312,6 +312,11 @@ class OracleFluid:
     def clearPressure(self):
         self.p[...] = 0
 
+    def project(self, numIters, dt):
+        """fill(p, 0) + makeIncompressible as Simulate runs them (fluid.go:83, 90)."""
+        self.clearPressure()
+        self.makeIncompressible(numIters, dt)
+
     def solve_stats(self):
         c = self._f.contents
         return {"sweeps_run": c.last_iters, "last_max_div": c.last_maxdiv}

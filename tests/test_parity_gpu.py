@@ -528,6 +528,71 @@ def test_slab_decomposition_is_bit_identical(preset_name, nslabs, transport):
     single.close()
 
 
+def projection_case(size):
+    """BASELINE config 5 at a small size: SplitMix64 velocity field, obstacle lattice, walls, sources."""
+    from fluid_b200 import presets
+    p = presets.projection_stress(*size)
+    u, v = presets.projection_fields(size[0] + 2, size[1] + 2, 0, size[0] + 2)
+
+    def prepare(f):
+        f.set("U", u); f.set("V", v)
+        f.edit(p.init); f.edit(p.per_step)
+    return p, prepare
+
+
+@pytest.mark.parametrize("size", [(256, 256), (600, 200)])
+def test_projection_stress_config5_parity_and_residual(size):
+    """configs[4] input at a size the oracle finishes at once: fb_phase(PROJECT) of the
+    pressure-form solver == its CPU restatement bit for bit (U, V, p), and the residual criterion of
+    the north star: max|div| after the 8 red-black iterations <= the reference's after its 8
+    lexicographic sweeps on the same input."""
+    import fluid_b200
+    import oracle
+    p, prepare = projection_case(size)
+    lex = oracle.New(p.density, p.width, p.height, p.h, solver=oracle.SOLVER_EXACT)
+    cpu = oracle.New(p.density, p.width, p.height, p.h, solver=oracle.SOLVER_REDBLACK_PRESSURE)
+    g = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
+    for f in (lex, cpu, g):
+        prepare(f)
+    for name in ("U", "V", "S"):
+        assert_bit_exact(f"config5 input:{name}", g.get(name), cpu.get(name))
+    before = lex.MaxDivergence()
+    assert np.float32(g.MaxDivergence()) == np.float32(before)
+    for f in (lex, cpu, g):
+        f.project(8, p.dt)
+    assert_state_equal(g, cpu, "config5 project", fields=("U", "V", "p"))
+    after_lex, after_gpu = lex.MaxDivergence(), g.MaxDivergence()
+    assert after_gpu <= after_lex < before, (before, after_lex, after_gpu)
+    # a second solve starts from p = 0 again (Simulate's fill) and keeps converging
+    cpu.project(8, p.dt); g.project(8, p.dt)
+    assert_state_equal(g, cpu, "config5 project x2", fields=("U", "V", "p"))
+    assert g.MaxDivergence() < after_gpu
+    g.close()
+
+
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_projection_on_slabs_is_bit_identical(nslabs):
+    """The strong-scaling path of bench.py --workload project*: ghost lines of U, V refreshed, then
+    fb_phase(PROJECT) on every slab -- same bits as the single-domain solve, solve after solve."""
+    import fluid_b200
+    from fluid_b200.parallel import LocalSlabGroup
+    p, prepare = projection_case((512, 160))
+    single = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
+    prepare(single)
+    group = LocalSlabGroup(p.density, p.width, p.height, p.h, nslabs, solver=2, ghost=32, reach=1)
+    u, v = single.get("U"), single.get("V")
+    for s in group.slabs:
+        s.f.set("U", u); s.f.set("V", v)
+        s.f.edit(p.init)
+    for k in range(3):
+        single.project(8, p.dt)
+        group.project(8, p.dt)
+        for name in ("U", "V", "p"):
+            assert_bit_exact(f"config5 slabs solve {k}:{name}", group.get(name), single.get(name))
+    group.close()
+    single.close()
+
+
 def test_step_local_single_rank_equals_step():
     import fluid_b200
     from fluid_b200 import presets
