@@ -74,9 +74,7 @@
 #define RQ_SW (RQ_NIT * RQ_SPLIT)   // sweep warps
 #define RQ_LW 4           // loader warps (line-interleaved)
 #define RQ_WW 4           // writer warps (line-interleaved)
-#define RQ_P1 (32 * (RQ_SW + RQ_LW + RQ_WW))   // producer 1 (TMA for the loader)
-#define RQ_P2 (RQ_P1 + 32)                      // producer 2 (TMA for the writer)
-#define RQ_THREADS (RQ_P2 + 32)
+#define RQ_THREADS (32 * (RQ_SW + RQ_LW + RQ_WW))
 #define RQ_WL 512         // columns per slot, whatever TJ is: every lane of a sweep always owns its groups of four cells
 #define RQ_TJ_MAX 464     // multiple of 16; TJ + 2 * RQ_H + 16 <= RQ_WL (16-byte granules for the TMA copies of the mask)
 #ifndef RQ_STG
@@ -430,6 +428,34 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const int live_lo = max(1, g.i_alloc0) - e0;
         const int live_hi = min(min(NX - 2, g.i_alloc0 + g.lines_alloc - 2), e1 - 1) - e0;
         const unsigned b_full = rq_s32(full), ring_last = rq_s32(bars + nit * RQ_RING);
+        // TMA: lane 0 of the warp that has just consumed staging slot k refills it with the line RQ_STG further on (its
+        // own next-but-one line: RQ_STG is a multiple of RQ_LW).  A single producer thread for all lines was the
+        // bottleneck of the whole pipeline: ~700 cycles per line for wait + proxy fence + three bulk copies.
+        const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
+        const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
+        const int off = cj0 - jr0;                                            // staging column of global column cj0
+        const unsigned bU = (unsigned)(cjU - cj0) * 4, bV = (unsigned)(cjV - cj0) * 4, bM = (unsigned)(cjU - cj0);
+        // lines that exist in this rank's planes: relative [relA, relB)
+        const int relA = max(0, g.i_alloc0) - e0, relB = (cjU > cj0 && !(P.xflags & 4)) ? min(NX, g.i_alloc0 + g.lines_alloc) - e0 : -1;
+        const long long o0 = (long long)(e0 - g.i_alloc0) * PIT + cj0;       // offset of relative line 0 (may be negative)
+        auto stage_line = [&](int line) {                                    // one lane: line -> staging slot line % RQ_STG
+            const int k = line & (RQ_STG - 1);
+            unsigned char *sk = stg + k * STG;
+            const unsigned fb = rq_s32(full + k);
+            if (line >= relA && line < relB) {
+                const long long o = o0 + (long long)line * PIT;
+                // order the generic-proxy reads of this staging slot before the async-proxy writes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                rq_mbar_expect_tx(full + k, bU + bV + bM);
+                rq_tma_load(rq_s32(reinterpret_cast<float *>(sk) + off), P.U + o, bU, fb);
+                rq_tma_load(rq_s32(reinterpret_cast<float *>(sk) + WL + off), P.V + o, bV, fb);
+                rq_tma_load(rq_s32(sk + (size_t)(2 * WL + 4) * 4 + off), P.mask + o, bM, fb);
+            } else {
+                rq_mbar_arrive(full + k);
+            }
+        };
+        if (lane == 0)
+            for (int line = lw; line < RQ_STG && line <= nproc; line += RQ_LW) stage_line(line);
         int sl = lw;                                         // slot of line rel
         for (int rel = lw; rel <= nproc; rel += RQ_LW) {
             // slot(rel) last held line y-1 with y = rel - NL + 1.  Its readers: the stages up to the last one's step y
@@ -478,6 +504,12 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                 *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)__byte_perm(code, 0u, 0x4431);
             }
             rq_done_line(ring_ld, rel);
+            __syncwarp();                                    // every lane is done with staging slot st0
+            if (lane == 0 && rel + RQ_STG <= nproc) {
+                // the slot also was the "line above" of line rel-1, which another loader warp handles
+                if (rel >= 1) rq_wait_line(ring_ld, rel - 1, 35 << 20);
+                stage_line(rel + RQ_STG);
+            }
             sl += RQ_LW; if (sl >= RQ_NL) sl -= RQ_NL;
         }
     } else if (warp < RQ_SW + RQ_LW + RQ_WW) {
@@ -493,6 +525,28 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
         const bool turb = P.turb > 0.0f;
         const float cp = P.cp;
         const int oV = 4 * P.TJ;
+        // TMA of U0, V0, mask of the OWNED columns of an owned line into this warp's own staging slots (lane 0)
+        const int c0 = strip * P.TJ;                                          // first column the writer owns
+        const int nc = min(P.TJ, PIT - c0);                                   // multiple of 16 (pitch % 32 == 0)
+        const unsigned bF = (unsigned)nc * 4, bMk = (unsigned)nc;
+        const bool no_tma = (P.xflags & 4) || nc <= 0;
+        const long long ow0 = (long long)(i0c - g.i_alloc0) * PIT + c0;
+        auto stage_line = [&](int n) {
+            const int k = n & (RQ_WSTG - 1);
+            const unsigned sb = rq_s32(wstg + k * WSTGB), fb = rq_s32(wfull + k);
+            if (!no_tma) {
+                const long long o = ow0 + (long long)n * PIT;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                rq_mbar_expect_tx(wfull + k, 2 * bF + bMk);
+                rq_tma_load(sb, P.U + o, bF, fb);
+                rq_tma_load(sb + 4 * P.TJ, P.V + o, bF, fb);
+                rq_tma_load(sb + 8 * P.TJ, P.mask + o, bMk, fb);
+            } else {
+                rq_mbar_arrive(wfull + k);
+            }
+        };
+        if (lane == 0)
+            for (int n = ww; n < RQ_WSTG && n < i1c - i0c; n += RQ_WW) stage_line(n);
         for (int n = ww; n < i1c - i0c; n += RQ_WW) {
             const int r = i0c + n, rel = r - e0;
             rq_wait_line(ring_last, rel + 1, nst << 20);                // the last iteration has finished its step rel+1: line r is final
@@ -562,69 +616,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
                     for (int k = 0; k < 4 && w_j + k < NY; k++) { P.Uo[o + k] = pu[k]; P.Vo[o + k] = pv[k]; P.Po[o + k] = pp[k]; }
                 }
             }
-            rq_done_line(ring_wr, rel);                               // slots and staging of line r are free
+            rq_done_line(ring_wr, rel);                               // the slots of line r are free
+            __syncwarp();
+            if (lane == 0 && n + RQ_WSTG < i1c - i0c) stage_line(n + RQ_WSTG);
             sl += RQ_WW; if (sl >= RQ_NL) sl -= RQ_NL;
-        }
-    } else if (tid == RQ_P2) {
-        // ================= second producer: U0, V0, mask of the owned lines for the writer =================
-        const int c0 = strip * P.TJ;                                          // first column the writer owns
-        const int nc = min(P.TJ, PIT - c0);                                   // multiple of 16 (pitch % 32 == 0)
-        const unsigned bF = (unsigned)nc * 4, bM = (unsigned)nc, bytes = 2 * bF + bM;
-        const bool skip = (P.xflags & 4) || nc <= 0;
-        const long long o0 = (long long)(i0c - g.i_alloc0) * PIT + c0;
-        const float *gU = P.U + o0, *gV = P.V + o0;
-        const unsigned char *gM = P.mask + o0;
-        int ws = 0;
-        for (int n = 0; n < i1c - i0c; n++) {
-            // the writer warp that had this staging slot (line n - RQ_WSTG) is done with it
-            if (n >= RQ_WSTG) rq_wait_line(ring_wr, own0 + n - RQ_WSTG, 33 << 20);
-            const unsigned sb = rq_s32(wstg + ws * WSTGB), fb = rq_s32(wfull + ws);
-            if (!skip) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                rq_mbar_expect_tx(wfull + ws, bytes);
-                rq_tma_load(sb, gU, bF, fb);
-                rq_tma_load(sb + 4 * P.TJ, gV, bF, fb);
-                rq_tma_load(sb + 8 * P.TJ, gM, bM, fb);
-            } else {
-                rq_mbar_arrive(wfull + ws);
-            }
-            gU += PIT; gV += PIT; gM += PIT;
-            if (++ws == RQ_WSTG) ws = 0;
-        }
-    } else if (tid == RQ_P1) {
-        // ================= producer: TMA bulk copies into the staging ring =================
-        // line rel goes to staging slot rel % RQ_STG once the loader is past lines rel - RQ_STG and
-        // rel - RQ_STG - 1 (the loader reads staging slot(rel) for lines rel-1 and rel; this loop has
-        // waited for the earlier line one trip ago).
-        const int cj0 = jr0 < 0 ? 0 : jr0;                                   // first global column copied
-        const int cjU = min(jr0 + WL, PIT), cjV = min(jr0 + WL + 4, PIT);    // one past the last column (U, mask / V)
-        const int off = cj0 - jr0;                                            // staging column of global column cj0
-        const unsigned bU = (unsigned)(cjU - cj0) * 4, bV = (unsigned)(cjV - cj0) * 4, bM = (unsigned)(cjU - cj0);
-        const unsigned bytes = bU + bV + bM;
-        // lines that exist in this rank's planes: relative [relA, relB)
-        const int lineA = max(0, g.i_alloc0), lineB = min(NX, g.i_alloc0 + g.lines_alloc);
-        const int relA = lineA - e0, relB = (cjU > cj0 && !(P.xflags & 4)) ? lineB - e0 : -1;
-        const long long o0 = (long long)(e0 - g.i_alloc0) * PIT + cj0;       // offset of relative line 0 (may be negative)
-        const float *gU = P.U + o0, *gV = P.V + o0;
-        const unsigned char *gM = P.mask + o0;
-        for (int rel = 0; rel <= nproc; rel++) {
-            const int k = rel & (RQ_STG - 1);
-            if (rel >= RQ_STG) {
-                rq_wait_line(ring_ld, rel - RQ_STG, 34 << 20);
-            }
-            unsigned char *s0 = stg + k * STG;
-            const unsigned fb = rq_s32(full + k);
-            if (rel >= relA && rel < relB) {
-                // order prior generic-proxy reads of this staging slot before the async-proxy writes
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                rq_mbar_expect_tx(full + k, bytes);
-                rq_tma_load(rq_s32(reinterpret_cast<float *>(s0) + off), gU, bU, fb);
-                rq_tma_load(rq_s32(reinterpret_cast<float *>(s0) + WL + off), gV, bV, fb);
-                rq_tma_load(rq_s32(s0 + (size_t)(2 * WL + 4) * 4 + off), gM, bM, fb);
-            } else {
-                rq_mbar_arrive(full + k);
-            }
-            gU += PIT; gV += PIT; gM += PIT;
         }
     }
 }

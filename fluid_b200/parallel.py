@@ -203,6 +203,7 @@ class SlabFluid:
         return regions
 
     def exchange(self):
+        self._ghost_stale = False
         if self.nranks == 1:
             return
         if self.transport == "peer":
@@ -237,6 +238,7 @@ class SlabFluid:
             raise ValueError("a slab solve is one pass of at most 8 iterations between halo exchanges")
         self.exchange()
         self.f.project(numIters, dt)
+        self._ghost_stale = True      # only owned lines are solved: the ghost lines now lag one solve behind
 
     def check_halo(self):
         self._steps_since_check = 0
@@ -251,6 +253,8 @@ class SlabFluid:
         return float(t.item())
 
     def MaxDivergence(self) -> float:
+        if getattr(self, "_ghost_stale", False):
+            self.exchange()           # the divergence of the last owned line reads the first ghost line
         return self._allreduce(self.f.MaxDivergence(), self.dist.ReduceOp.MAX)
 
     def max_speed(self) -> float:

@@ -57,6 +57,37 @@ def main():
             single.close()
         slab.close()
         dist.barrier()
+    # BASELINE config 5: projection only on the slabs (ghost lines of U, V refreshed before every solve)
+    for transport in ("peer", "nccl"):
+        size = (192 * world, 224)
+        p = presets.projection_stress(*size)
+        u, v = presets.projection_fields(size[0] + 2, size[1] + 2, 0, size[0] + 2)
+        slab = SlabFluid(p.density, p.width, p.height, p.h, solver=2, device=local, rank=rank, nranks=world,
+                         ghost=32, reach=1, transport=transport)
+        slab.f.set("U", u); slab.f.set("V", v)
+        slab.edit(p.init); slab.edit(p.per_step)
+        divs = []
+        for _ in range(3):
+            slab.project(8, p.dt)
+            divs.append(slab.MaxDivergence())
+        fields = {name: slab.get(name) for name in ("U", "V", "p")}
+        if rank == 0:
+            single = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2, device=local)
+            single.set("U", u); single.set("V", v)
+            single.edit(p.init); single.edit(p.per_step)
+            want_divs = []
+            for _ in range(3):
+                single.project(8, p.dt)
+                want_divs.append(single.MaxDivergence())
+            for name, got in fields.items():
+                bad = int(np.count_nonzero(got != single.get(name)))
+                print(f"[projection {size[0]}x{size[1]} {transport}] {name}: mismatches={bad}")
+                failures += bad != 0
+            print(f"[projection {transport}] max|div| after 1..3 solves: {divs} (single GPU: {want_divs})")
+            failures += [np.float32(x) for x in divs] != [np.float32(x) for x in want_divs]
+            single.close()
+        slab.close()
+        dist.barrier()
     t = torch.tensor([failures], device="cuda")
     dist.broadcast(t, 0)
     dist.destroy_process_group()
