@@ -15,30 +15,30 @@
 //
 // Structure: a CTA owns `chunk` lines x TJ columns (+16-cell halo, recomputed).  Lines
 // (constant i, contiguous in j) stream through a ring of RQ_NL slots in shared memory
-// (q, -D0, neighbour count: 9 B per cell, 512 columns per slot).  The warps form a software
+// (q, -D0, neighbour count: 9 B per cell, 512 columns per slot).  24 warps form a software
 // pipeline WITHOUT block-wide barriers:
-//   producer 1   one thread: TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the U, V,
-//                mask segments of a line into an RQ_STG-deep staging ring, ahead of the loader
-//   loader       4 warps, line-interleaved (warp k: lines k, k+4, ...): staging -> -D0, neighbour
-//                count (bits 5-7 of the mask byte), q = 0 in slot(line)
-//   stage t < 8  ITERATION t, RQ_SPLIT warps side by side.  Step `rel` is the red half sweep on
-//                line rel ("first") followed by the black half sweep on line rel-1 ("second");
-//                both touch the columns of one parity.  Everything `second` needs is in
-//                registers: its own vector is the `dn` of `first` (the `up` loaded two steps ago),
-//                its `up` is the result of `first`, left / right and `dn` are the results of the
-//                two previous steps; `first` reads only its own vector and the line above.  A
-//                stage may run step rel once its predecessor has finished step rel+2.
-//   producer 2   one thread: TMA bulk copies of U0, V0, mask of the OWNED columns of the owned
-//                lines into an RQ_WSTG-deep ring for the writer
-//   writer       4 warps, line-interleaved: slot(r), slot(r-1) + U0, V0, mask -> U, V, p in global
-// Hand-offs are PROGRESS COUNTERS in shared memory (one per warp: "steps / lines I have
-// finished"), published by lane 0 with st.release after a __syncwarp and polled by every lane of
-// the consumer with ld.acquire: a poll is an LDS (~30 cycles).  Only the TMA completions are
-// mbarriers.  Waits are bounded: a pipeline that stops latches a debug record and the host
-// returns FB_ERR_CUDA instead of hanging the GPU.
+//   loader       4 warps, line-interleaved (warp k: lines k, k+4, ...): TMA staging -> -D0, neighbour
+//                count (bits 5-7 of the mask byte), q = 0 in slot(line).  Lane 0 of the warp that
+//                has consumed a staging slot refills it with the line RQ_STG further on: bulk copies
+//                (cp.async.bulk + mbarrier complete_tx) of the U, V, mask segments of that line
+//   stage t < 8  ITERATION t, RQ_SPLIT = 2 warps side by side (128 same-parity cells each, 4 per lane).
+//                Step `rel` is the red half sweep on line rel ("first") followed by the black half
+//                sweep on line rel-1 ("second"); both touch the columns of one parity.  Everything
+//                `second` needs is in registers: its own vector is the `dn` of `first` (the `up` loaded
+//                two steps ago), its `up` is the result of `first`, left / right and `dn` are the
+//                results of the two previous steps; `first` reads only its own vector and the line
+//                above.  The neighbour beyond a lane's four cells comes from the next lane by shuffle.
+//                A stage may run step rel once its predecessor has finished step rel+2; the two warps
+//                of a stage meet at a named barrier (bar.sync) once per step
+//   writer       4 warps, line-interleaved: slot(r), slot(r-1) + U0, V0, mask (its own TMA staging
+//                ring, refilled by lane 0 of the warp that owns the slot) -> U, V, p in global
+// Hand-offs are per-line mbarriers (a ring of 64 per role; every lane of the warp(s) that own the
+// line arrives, every lane of a consumer polls with try_wait); the loader reuses a slot once the
+// writer (or, for halo lines, the last iteration) is past it.  Waits are bounded: a pipeline that
+// stops latches a debug record and the host returns FB_ERR_CUDA instead of hanging the GPU.
 // Even and odd columns live in separate arrays so one colour is contiguous: a lane updates 4
-// consecutive same-colour cells per group with LDS.128 / STS.128 and packed FADD2 / FFMA2
-// (sm_100a fp32x2, bit-identical to the scalar operations).
+// consecutive same-colour cells with LDS.128 / STS.128 and packed FADD2 / FFMA2 (sm_100a fp32x2,
+// bit-identical to the scalar operations).
 //
 // Why this shape (ncu, 4098^2, 8 iterations; time of the solve):
 //   face form (rb_fused.cuh), ~110 instructions per cell update, issue-bound          1.11 ms
@@ -46,18 +46,24 @@
 //   one warp per half sweep, per-line mbarrier hand-offs, strips x chunks = one wave  0.31
 //   writer inputs through TMA (its re-read of U0, V0 missed L2 two times in three)    0.226
 //   neighbour counts baked into the mask, lean loader / writer loops                  0.211
-//   one warp per iteration (two half sweeps fused, neighbours carried in registers)   0.208
-//   What bounded all of these was not instructions but the LATENCY of a hand-off: with every
-//   role's work switched off (FLUIDB200_RBQ_X=31) the mbarrier skeleton alone took 0.077 ms --
-//   mbarrier.try_wait costs ~115 cycles per poll and each line crosses 10 hand-offs inside a
-//   ring that is only 11 lines deeper than the pipeline.  Sleeping pollers changed nothing.
-//   line-interleaved loader / writer warps (four line periods per line)               0.223 (floor 0.124 -> 0.083)
-//   two warps per stage (half the columns each)                                       0.192
-//   progress counters instead of mbarriers: see profiles/
-// Measured and NOT adopted: one arrive per warp instead of 32 (no change); 2-instruction poll loop
-// (slower); nanosleep after a failed poll (no change); deeper rings or staging (no change);
-// re-reading the neighbour vectors instead of carrying them (LSU pipe 79 %); turbulence fused
-// into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2).
+//   one warp per iteration (two half sweeps fused, neighbours carried in registers):
+//   2.5 LDS.128 per four updates instead of 5, 8 pipeline stages instead of 16        0.208
+//   line-interleaved loader / writer warps (four line periods per line) + two warps
+//   per stage: the time with the sweeps switched off fell 0.148 -> 0.120              0.191
+//   edge neighbours by shuffle (the scalar LDS at a 16-byte stride was a 4-way bank
+//   conflict: 8 of a step's 34 shared-memory wavefronts)                              0.188
+//   TMA issued by the loader / writer warps (a single producer thread spent ~700
+//   cycles per line on wait + proxy fence + three bulk copies)                        0.182
+// Where the time goes now (profiles/): shared-memory wavefronts 68 % of peak (721 per line: 448 the
+// sweeps, the rest TMA, loader, writer), issue slots 65 %; with ONE iteration the kernel takes
+// 0.120 ms (writer warps 90 % busy), every further iteration adds ~0.01 ms.
+// Measured and NOT adopted (FLUIDB200_RBQ_X switches roles off for such experiments):
+//   progress counters in shared memory polled with LDS instead of mbarriers: 0.224 (a poll every
+//   ~40 cycles per waiting warp is shared-memory traffic; try_wait suspends the warp ~100 cycles);
+//   sleeping after a failed poll, a non-blocking test_wait first, one arrive per warp: no change;
+//   issuing the loads of lines rel, rel-1 before the hand-off wait: 0.195; 24 / 32 ring slots,
+//   deeper staging: no change; re-reading the neighbour vectors instead of carrying them (LSU
+//   pipe 79 %); turbulence fused into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2).
 #pragma once
 #include "kernels.cuh"
 #include "advect_fused.cuh"
@@ -84,7 +90,7 @@
 #define RQ_WSTG 8         // writer staging ring depth; power of two
 #endif
 // shared memory at TJ = 464: 28 slots * 512 * 9 B (q, -D0, neighbour count) = 126 KB, loader staging
-// 8 * (512*9 + 16) B = 36.1 KB, writer staging 8 * 464 * 9 B = 32.6 KB, mbarriers, wd/s table, counters: 196 KB
+// 8 * (512*9 + 16) B = 36.1 KB, writer staging 8 * 464 * 9 B = 32.6 KB, hand-off mbarriers 5 KB, wd/s table: 200 KB
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
 __host__ __device__ __forceinline__ size_t rq_wstage_bytes(int TJ) { return (size_t)TJ * 9; }   // U0, V0, mask of TJ columns
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL, int TJ)
@@ -263,6 +269,9 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
                                              const float4 (&F1)[RQ_Q])
 {
     {   // the loader has finished line rel+1 / the previous iteration has finished its step rel+2
+        // (the loader's warps take the lines in turn, so "line 1 is loaded" says nothing about line 0: the
+        // first step of the first iteration waits for both; every later line was waited for one step earlier)
+        if (!SECOND && S.lag == 1) rq_wait_line(S.pred, 0, S.tag);
         rq_wait_line(S.pred, min(rel + S.lag, S.nproc), S.tag);
     }
     // the stores of the previous step by the other lanes of the stage (left / right neighbours of `second`)
