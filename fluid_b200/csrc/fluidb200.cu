@@ -5,6 +5,7 @@
 #include "advect_fused.cuh"
 #include "rb_fused.cuh"
 #include "rbq_fused.cuh"
+#include "multigrid.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -44,6 +45,8 @@ struct fb_handle {
     // exact-solver scheduling state
     int2 *d_order; int ntiles, nTa, nTb, order_T;
     int *d_tile_counter; int *d_done; int epoch;
+    // multigrid V-cycle: coarse grid (fluid.go:632-633) and its three arrays, allocated on first use
+    CoarseGrid cg; float *mg_rhs, *mg_cS, *mg_cP;
     fb_edit_cmd *d_cmds; size_t d_cmds_cap;
     std::vector<fb_edit_cmd> staged_cmds;   // host copy of what d_cmds holds (per-step lists repeat)
     cudaEvent_t ev0, ev1;
@@ -236,6 +239,9 @@ extern "C" int fb_destroy(fb_handle *h)
     if (h->d_tile_counter) cudaFree(h->d_tile_counter);
     if (h->d_done) cudaFree(h->d_done);
     if (h->d_cmds) cudaFree(h->d_cmds);
+    if (h->mg_rhs) cudaFree(h->mg_rhs);
+    if (h->mg_cS) cudaFree(h->mg_cS);
+    if (h->mg_cP) cudaFree(h->mg_cP);
     for (auto &pr : h->prof_pairs) { cudaEventDestroy(pr.second.first); cudaEventDestroy(pr.second.second); }
     for (auto e : h->prof_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -608,14 +614,97 @@ static int read_stats(fb_handle *h, unsigned iters)
 
 static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext = 0);
 
+// solveMultigridVCycle (fluid.go:560-599): per cycle 3 smoothing sweeps at 1.5, residual ->
+// restriction -> 40 coarse sweeps at 1.6 -> prolongation -> correction, 3 smoothing sweeps at 1.2.
+// FB_SOLVER_EXACT runs every sweep (fine and coarse) in the reference's lexicographic order
+// through wavefronts and is bit-identical to the reference; the red-black solvers run the same
+// cycle with red-black sweeps on both levels.  stats: max_div[k] = max|div| of the third
+// pre-smoothing sweep of cycle k (the value fluid.go:575 tests), sweeps_run = cycles entered.
+static int solve_multigrid_vcycle(fb_handle *h, const fb_params *p, float dt, unsigned iters)
+{
+    if (h->cfg.nranks > 1) return fail(h, FB_ERR_UNSUPPORTED, "the multigrid V-cycle is single-GPU only");
+    const Grid &g = h->g;
+    CoarseGrid &c = h->cg;
+    if (!h->mg_rhs) {
+        c.NX = (g.NX + 1) / 2; c.NY = (g.NY + 1) / 2;      // fluid.go:632-633
+        c.pitch = cdiv(c.NY, 32) * 32;
+        const size_t bytes = (size_t)c.NX * (size_t)c.pitch * sizeof(float);
+        CK(cudaMalloc(&h->mg_rhs, bytes)); CK(cudaMalloc(&h->mg_cS, bytes)); CK(cudaMalloc(&h->mg_cP, bytes));
+    }
+    const bool exact = p->solver == FB_SOLVER_EXACT;
+    SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    for (int k = 0; k < 3; k++) { sp.omega[k] = 1.5f; sp.omega[3 + k] = 1.2f; }   // fluid.go:574, 596
+    sp.damping = p->pressure_damping;
+    { volatile float dh = h->cfg.density * h->cfg.h; sp.cp = dh / dt; }           // fluid.go:561
+    const float tolerance = 1e-5f;
+    const int coarse_iters = 40;              // fluid.go:689
+    const float coarse_relaxation = 1.6f;     // fluid.go:690
+    h->stats.sweeps_run = 0;
+    h->stats.rolled_back = 0;
+    for (unsigned k = 0; k < 32; k++) h->stats.max_div[k] = 0.0f;
+    if (iters == 0) return FB_OK;
+    h->p_zero = false;
+
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 rb_grid, rb_block;
+    plane_launch(g, ib, ie, rb_grid, rb_block, g.NY / 2 + 1);
+    // three fine-grid sweeps with omega[first .. first+3), max|div| per sweep into d_red[first + s]
+    auto smooth = [&](int first) -> int {
+        if (exact) return exact_sweeps(h, sp, first, 3);
+        for (int s = 0; s < 3; s++)
+            for (int colour = 0; colour < 2; colour++) {
+                k_redblack_half<<<rb_grid, rb_block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P], colour,
+                                                                     sp.omega[first + s], sp.damping, sp.cp, h->d_red + first + s, ib, ie);
+                CKL("k_redblack_half");
+            }
+        return FB_OK;
+    };
+    const dim3 blk(128, 2, 1);
+    for (unsigned iter = 0; iter < iters; iter++) {
+        CK(cudaMemsetAsync(h->d_red, 0, 32 * sizeof(unsigned), h->stream));
+        TRY(smooth(0));
+        CK(cudaMemcpyAsync(h->h_red, h->d_red, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float maxDiv; memcpy(&maxDiv, &h->h_red[2], 4);
+        h->stats.max_div[iter] = maxDiv;
+        h->stats.sweeps_run = (int)iter + 1;
+        if (maxDiv < tolerance) break;                                            // fluid.go:575-577
+
+        k_mg_restrict<<<dim3(cdiv(c.NY, blk.x), cdiv(c.NX, blk.y)), blk, 0, h->stream>>>(g, c, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P],
+                                                                                        h->mg_rhs, h->mg_cS, h->mg_cP);
+        CKL("k_mg_restrict");
+        if (exact) {
+            const int tau_last = (c.NX - 2) + (c.NY - 2) + 2 * (coarse_iters - 1);
+            const dim3 dgrid(cdiv(c.NX - 2 > 0 ? c.NX - 2 : 1, 128), coarse_iters);
+            if (c.NX > 2 && c.NY > 2)
+                for (int tau = 2; tau <= tau_last; tau++) {
+                    k_mg_coarse_diag<<<dgrid, 128, 0, h->stream>>>(c, h->mg_cP, h->mg_cS, h->mg_rhs, tau, coarse_iters, coarse_relaxation);
+                    CKL("k_mg_coarse_diag");
+                }
+        } else {
+            const dim3 cgrid(cdiv(c.NY / 2 + 1, blk.x), cdiv(c.NX - 2 > 0 ? c.NX - 2 : 1, blk.y));
+            for (int it = 0; it < coarse_iters; it++)
+                for (int colour = 0; colour < 2; colour++) {
+                    k_mg_coarse_redblack<<<cgrid, blk, 0, h->stream>>>(c, h->mg_cP, h->mg_cS, h->mg_rhs, colour, coarse_relaxation);
+                    CKL("k_mg_coarse_redblack");
+                }
+        }
+        k_mg_apply<<<dim3(cdiv(g.NY, blk.x), cdiv(g.NX, blk.y)), blk, 0, h->stream>>>(g, c, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P],
+                                                                                     h->mg_cP, sp.cp);
+        CKL("k_mg_apply");
+        TRY(smooth(3));
+    }
+    return FB_OK;
+}
+
 // makeIncompressible (fluid.go:144-155) + solveSingleGrid (fluid.go:157-186)
 static int make_incompressible(fb_handle *h, const fb_params *p, float dt, unsigned iters)
 {
-    if (p->use_multigrid && p->multigrid_levels > 1)
-        return fail(h, FB_ERR_UNSUPPORTED, "multigrid V-cycle (fluid.go:560-758) is out of scope for this build");
     if (iters > 32) return fail(h, FB_ERR_INVALID, "at most 32 sweeps per solve");
     TRY(copy_border(h, h->f[FB_NEWU], h->f[FB_U]));
     TRY(copy_border(h, h->f[FB_NEWV], h->f[FB_V]));
+    if (p->use_multigrid && p->multigrid_levels > 1) return solve_multigrid_vcycle(h, p, dt, iters);   // fluid.go:148-150
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
     if (p->solver == FB_SOLVER_EXACT) omega_schedule(p, iters, sp.omega);
@@ -1258,7 +1347,8 @@ extern "C" int fb_step(fb_handle *h, const fb_params *p, float dt, int32_t nstep
             continue;
         }
         // fused path: same phase order, same arithmetic, fewer passes over HBM
-        const bool rb = p->solver != FB_SOLVER_EXACT;
+        const bool mg = p->use_multigrid && p->multigrid_levels > 1;   // V-cycle: unfused sweeps that read p
+        const bool rb = p->solver != FB_SOLVER_EXACT && !mg;
         const bool conf = p->confinement != 0.0f, turb = p->turbulence_strength > 0.0f;
         if (rb) h->p_zero = true;                       // fill(p, 0) is folded into the fused solve
         else { ProfScope ps(h, FB_PROF_CLEAR_PRESSURE); TRY(clear_pressure(h)); }
@@ -1309,6 +1399,7 @@ extern "C" int fb_step_local(fb_handle *h, const fb_params *p, float dt, int32_t
         return fail(h, FB_ERR_UNSUPPORTED, "the lexicographic solver does not decompose into slabs; use a red-black solver");
     if (h->literal) return fail(h, FB_ERR_UNSUPPORTED, "slab steps use the fused path");
     if (p->viscosity_diffusion > 0.0f) return fail(h, FB_ERR_UNSUPPORTED, "viscosity is not available in slab steps");
+    if (p->use_multigrid && p->multigrid_levels > 1) return fail(h, FB_ERR_UNSUPPORTED, "the multigrid V-cycle is not available in slab steps");
     if (n_per_step) for (size_t q = 0; q < n_per_step; q++) TRY(validate_cmd(h, per_step[q]));
     const unsigned iters = p->iters > 0 ? (unsigned)p->iters : 8u;
     if (iters > 8) return fail(h, FB_ERR_UNSUPPORTED, "slab steps fuse at most 8 iterations (one pass)");
@@ -1380,7 +1471,7 @@ extern "C" int fb_phase(fb_handle *h, int32_t phase, const fb_params *p, float d
     case FB_PHASE_CLEAR_PRESSURE: return clear_pressure(h);
     case FB_PHASE_PROJECT: {
         ProfScope ps(h, FB_PROF_PROJECT);
-        if (h->literal || p->solver == FB_SOLVER_EXACT || iters == 0) TRY(clear_pressure(h));
+        if (h->literal || p->solver == FB_SOLVER_EXACT || iters == 0 || (p->use_multigrid && p->multigrid_levels > 1)) TRY(clear_pressure(h));
         else h->p_zero = true;                         // the fused red-black solvers never read a zero pressure
         return make_incompressible(h, p, dt, iters);
     }

@@ -14,17 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/fluidb200.h"
-
-struct Grid {
-    int NX, NY;        // global NumX, NumY (fluid.go:48-49)
-    int pitch;         // floats per allocated line
-    int i_alloc0;      // global i of allocated line 0
-    int lines_alloc;   // allocated lines
-    int i_lo, i_hi;    // owned global lines [i_lo, i_hi)
-    __host__ __device__ __forceinline__ size_t at(int i, int j) const {
-        return (size_t)(i - i_alloc0) * (size_t)pitch + (size_t)j;
-    }
-};
+#include "grid.cuh"
 
 struct SolveParams {
     float omega[64];   // relaxation per sweep (exact) or per half sweep (red-black)

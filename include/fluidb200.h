@@ -90,7 +90,8 @@ typedef struct fb_params {
     float pressure_damping;      /* 1 */
     float turbulence_strength;   /* 0.02 */
     float smoke_advection;       /* 1 */
-    int32_t use_multigrid;       /* false; true is FB_ERR_UNSUPPORTED (out of scope) */
+    int32_t use_multigrid;       /* false (fluid.go:64).  With multigrid_levels > 1 makeIncompressible runs
+                                  * solveMultigridVCycle (fluid.go:560-599): `iters` V-cycles.  Single GPU only. */
     int32_t multigrid_levels;    /* 2 */
     int32_t use_bfecc;           /* false */
     int32_t solver;              /* fb_solver */
@@ -148,9 +149,11 @@ typedef enum fb_reduce_kind {
 } fb_reduce_kind;
 
 typedef struct fb_solve_stats {
-    int32_t sweeps_run;       /* sweeps executed by the last solve (early exit, fluid.go:175) */
+    int32_t sweeps_run;       /* sweeps executed by the last solve (early exit, fluid.go:175);
+                               * multigrid: V-cycles entered (early exit, fluid.go:575) */
     int32_t rolled_back;      /* exact solver: 1 if the early exit forced a re-run */
-    float max_div[32];        /* max pre-update |div| seen in each sweep (fluid.go:209-216) */
+    float max_div[32];        /* max pre-update |div| seen in each sweep (fluid.go:209-216);
+                               * multigrid: that of the third pre-smoothing sweep of each cycle */
 } fb_solve_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

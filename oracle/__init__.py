@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
             "fo_run": (C.c_int, [P, C.c_float, C.c_int64, C.c_void_p, C.c_int64]),
             "fo_project_redblack": (C.c_float, [P, C.c_uint, C.c_float]),
             "fo_project_redblack_q": (C.c_float, [P, C.c_uint, C.c_float]),
+            "fo_project_multigrid_redblack": (None, [P, C.c_uint, C.c_float]),
+            "fo_project_redblack_sched": (C.c_float, [P, C.c_void_p, C.c_uint, C.c_float]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(l, name)
@@ -229,6 +231,8 @@ class OracleFluid:
 
     # ---- hot path
     def _project_rb(self, iters, dt):
+        if self.UseMultigrid and self.MultigridLevels > 1:
+            return self._l.fo_project_multigrid_redblack(self._f, iters, dt)
         fn = self._l.fo_project_redblack_q if self.Solver == SOLVER_REDBLACK_PRESSURE else self._l.fo_project_redblack
         return fn(self._f, iters, dt)
 
@@ -278,6 +282,11 @@ class OracleFluid:
             self._project_rb(numIters, dt)
         else:
             self._l.fo_make_incompressible(self._f, numIters, dt)
+
+    def redblackIteration(self, relaxation, dt):
+        """NOT in the reference: one red + one black half sweep at `relaxation` (cp = density*h/dt)."""
+        om = np.array([relaxation, relaxation], dtype=np.float32)
+        return self._l.fo_project_redblack_sched(self._f, om.ctypes.data, 1, dt)
 
     def pressureIteration(self, relaxation, cp):
         return self._l.fo_pressure_iteration(self._f, relaxation, cp)

@@ -309,7 +309,10 @@ static float *restrict_residual(fo_fluid *f, const float *fine)
     return coarse;
 }
 
-static float *solve_coarse_grid(fo_fluid *f, const float *rhs)
+/* redblack = 0: the reference's lexicographic sweeps.  redblack = 1 (NOT in the reference): the
+ * same cell update, each sweep split into the (i+j) even cells then the odd ones -- the order of
+ * this repo's CUDA fast mode. */
+static float *solve_coarse_grid(fo_fluid *f, const float *rhs, int redblack)
 {
     const int64_t NX = f->NumX, NY = f->NumY;
     const int64_t cNX = (NX + 1) / 2, cNY = (NY + 1) / 2;
@@ -322,8 +325,10 @@ static float *solve_coarse_grid(fo_fluid *f, const float *rhs)
         }
     const float relaxation = 1.6f;
     for (int iter = 0; iter < 40; iter++)
+      for (int colour = 0; colour < (redblack ? 2 : 1); colour++)
         for (int64_t i = 1; i < cNX - 1; i++)
             for (int64_t j = 1; j < cNY - 1; j++) {
+                if (redblack && ((i + j) & 1) != colour) continue;
                 if (cS[i * cNY + j] == 0.0f) continue;
                 float sx0 = cS[(i - 1) * cNY + j], sx1 = cS[(i + 1) * cNY + j];
                 float sy0 = cS[i * cNY + j - 1], sy1 = cS[i * cNY + j + 1];
@@ -385,22 +390,46 @@ static void apply_pressure_correction(fo_fluid *f, const float *correction, floa
         }
 }
 
-static void solve_multigrid_vcycle(fo_fluid *f, unsigned numIters, float dt)
+static float redblack_half(fo_fluid *f, float relaxation, float cp, int colour);
+
+/* One fine-grid smoothing sweep: pressureJacobiIteration (fluid.go:188-234), or with redblack its
+ * two half sweeps (max |div| over both). */
+static float mg_smooth(fo_fluid *f, float relaxation, float cp, int redblack)
+{
+    if (!redblack) return fo_pressure_iteration(f, relaxation, cp);
+    float a = redblack_half(f, relaxation, cp, 0);
+    float b = redblack_half(f, relaxation, cp, 1);
+    return a > b ? a : b;
+}
+
+static void solve_multigrid_vcycle(fo_fluid *f, unsigned numIters, float dt, int redblack)
 {
     float cp = f->density * f->h / dt;
     const float tolerance = 1e-5f;
+    f->last_iters = 0;
+    f->last_maxdiv = 0.0f;
     for (unsigned iter = 0; iter < numIters; iter++) {
         float maxDiv = 0.0f;
-        for (unsigned s = 0; s < 3; s++) maxDiv = fo_pressure_iteration(f, 1.5f, cp);
+        for (unsigned s = 0; s < 3; s++) maxDiv = mg_smooth(f, 1.5f, cp, redblack);
+        f->last_iters = (int)iter + 1;      /* cycles entered */
+        f->last_maxdiv = maxDiv;            /* the value fluid.go:575 tests */
         if (maxDiv < tolerance) break;
         float *residual = compute_pressure_residual(f);
         float *coarseRHS = restrict_residual(f, residual);
-        float *coarseCorr = solve_coarse_grid(f, coarseRHS);
+        float *coarseCorr = solve_coarse_grid(f, coarseRHS, redblack);
         float *corr = prolongate_correction(f, coarseCorr);
         apply_pressure_correction(f, corr, cp);
-        for (unsigned s = 0; s < 3; s++) fo_pressure_iteration(f, 1.2f, cp);
+        for (unsigned s = 0; s < 3; s++) mg_smooth(f, 1.2f, cp, redblack);
         free(residual); free(coarseRHS); free(coarseCorr); free(corr);
     }
+}
+
+/* NOT in the reference: the V-cycle with red-black sweeps on both levels (see fluid_oracle.h). */
+void fo_project_multigrid_redblack(fo_fluid *f, unsigned iters, float dt)
+{
+    fo_copy_border(f, f->newU, f->U);
+    fo_copy_border(f, f->newV, f->V);
+    solve_multigrid_vcycle(f, iters, dt, 1);
 }
 
 /* ---- makeIncompressible (fluid.go:144-155) ------------------------------ */
@@ -408,7 +437,7 @@ void fo_make_incompressible(fo_fluid *f, unsigned iters, float dt)
 {
     fo_copy_border(f, f->newU, f->U);
     fo_copy_border(f, f->newV, f->V);
-    if (f->UseMultigrid && f->MultigridLevels > 1) solve_multigrid_vcycle(f, iters, dt);
+    if (f->UseMultigrid && f->MultigridLevels > 1) solve_multigrid_vcycle(f, iters, dt, 0);
     else solve_single_grid(f, iters, dt);
 }
 

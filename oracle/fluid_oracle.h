@@ -128,6 +128,10 @@ float fo_project_redblack(fo_fluid *f, unsigned iters, float dt);
  * against the frozen initial divergence D0, and U, V, p are materialised once at
  * the end.  Algebraically identical to fo_project_redblack; rounding differs. */
 float fo_project_redblack_q(fo_fluid *f, unsigned iters, float dt);
+/* NOT in the reference: solveMultigridVCycle (fluid.go:560-599) with every sweep -- the six
+ * fine-grid smoothing sweeps and the 40 coarse ones -- in red-black order; residual, restriction,
+ * prolongation and correction as in the reference.  Checks the CUDA fast-mode V-cycle bit for bit. */
+void fo_project_multigrid_redblack(fo_fluid *f, unsigned iters, float dt);
 /* Same with an explicit omega per HALF sweep: omega[2k] red, omega[2k+1] black. */
 float fo_project_redblack_sched(fo_fluid *f, const float *omega, unsigned iters, float dt);
 

@@ -1,0 +1,91 @@
+"""the multigrid V-cycle (fluid.go:560-758, 1123-1149) on the GPU,
+through the C ABI, against the oracle -- bit-exact float32, no tolerance.
+FB_SOLVER_EXACT reproduces the reference's lexicographic sweeps on both levels; the red-black
+solvers are checked against the oracle's red-black restatement of the same cycle."""
+import numpy as np
+import pytest
+
+from common import assert_bit_exact, copy_state
+from test_multigrid_cpu import scene
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_like(o, width, height, **kw):
+    import fluid_b200
+    g = fluid_b200.New(o.density, width, height, o.h, **kw)
+    copy_state(g, o)
+    g.UseMultigrid, g.MultigridLevels = True, 2
+    return g
+
+
+@pytest.mark.parametrize("literal", [False, True])
+@pytest.mark.parametrize("solver", [0, 1, 2])
+@pytest.mark.parametrize("width,height,zero_p", [(20, 15, True), (130, 67, False), (64, 64, True), (300, 257, True),
+                                                 (3, 3, False), (1, 1, False), (2, 5, True)])
+def test_vcycle_bit_exact(width, height, zero_p, solver, literal):
+    import oracle
+    dt = np.float32(1.0 / 60.0)
+    o = scene(oracle, width, height, 11, min(solver, 1), zero_p)      # pressure form: V-cycle sweeps are plain red-black
+    g = gpu_like(o, width, height, solver=solver, literal=literal)
+    o.makeIncompressible(3, dt)
+    g.makeIncompressible(3, dt)
+    for name in ("U", "V", "p"):
+        assert_bit_exact(f"{width}x{height}/solver{solver}:{name}", g.get(name), o.get(name))
+    so, sg = o.solve_stats(), g.solve_stats()
+    assert sg["sweeps_run"] == so["sweeps_run"]
+    assert np.float32(sg["max_div"][-1]) == np.float32(so["last_max_div"])
+    g.close()
+
+
+def test_vcycle_early_exit_matches():
+    """A divergence-free field leaves after the pre-smoothing of the first cycle (fluid.go:575)."""
+    import oracle
+    dt = np.float32(1.0 / 60.0)
+    o = scene(oracle, 40, 30, 5, 0, True)
+    o.U[...] = 0.0
+    o.V[...] = 0.0
+    g = gpu_like(o, 40, 30, solver=0)
+    o.makeIncompressible(4, dt)
+    g.makeIncompressible(4, dt)
+    assert g.solve_stats()["sweeps_run"] == o.solve_stats()["sweeps_run"] == 1
+    for name in ("U", "V", "p"):
+        assert_bit_exact(name, g.get(name), o.get(name))
+    g.close()
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_simulate_with_multigrid_bit_exact(solver):
+    """Whole steps with UseMultigrid (the scene of TestMultigridStability, fluid_test.go:1470-1547:
+    density 1, h 1, dt 0.08, viscosity, damping, confinement, jet, three obstacles)."""
+    import fluid_b200
+    import oracle
+    from fluid_b200 import edits as E
+    W, H = 30, 20
+    o = oracle.New(1.0, W, H, 1.0, solver=solver)
+    g = fluid_b200.New(1.0, W, H, 1.0, solver=solver)
+    c = (H + 2) // 2
+    init = [E.set_solid_rect(0, 0, W + 2, H + 2, False)] + [E.set_solid(i, j, True) for (i, j) in ((15, c), (22, c - 2), (22, c + 2))]
+    per_step = E.pack([E.set_velocity(3, j, 18.0, 0.0) for j in range(c - 3, c + 3)] +
+                      [E.cmd(E.SET_SMOKE, 3, c - 3, 4, c + 3, 1.0)])
+    for f in (o, g):
+        f.edit(E.pack(init))
+        f.UseMultigrid, f.MultigridLevels = True, 2
+        f.ViscosityDiffusion, f.PressureDamping, f.Confinement = 0.1, 0.95, 0.05
+    for step in range(12):
+        o.step(0.08, 1, per_step)
+        g.step(0.08, 1, per_step)
+        for name in ("U", "V", "p", "M"):
+            assert_bit_exact(f"step {step}:{name}", g.get(name), o.get(name))
+    assert np.isfinite(o.get("U")).all()
+    g.close()
+
+
+def test_multigrid_on_slabs_is_refused():
+    import fluid_b200
+    from fluid_b200._lib import FluidError
+    g = fluid_b200.New(1000.0, 64, 64, 0.01, solver=1, rank=0, nranks=2)
+    g.UseMultigrid = True
+    with pytest.raises(FluidError):
+        g.makeIncompressible(2, 1.0 / 60.0)
+    g.close()

@@ -327,8 +327,6 @@ def test_advanced_visual_enhancements(impl):
 @pytest.mark.parametrize("use_mg,iters", [(False, 8), (True, 4), (False, 4)])
 def test_multigrid_performance(impl, use_mg, iters):
     """TestMultigridPerformance (fluid_test.go:1024-1132): custom phase sequence."""
-    if use_mg and impl.kind == "gpu":
-        pytest.skip("multigrid V-cycle is out of scope for the CUDA path (SURVEY.md section 8f)")
     f = impl(1.0, 20, 15, 1.0)
     all_fluid(f)
     f.UseMultigrid = use_mg
@@ -502,8 +500,6 @@ def test_set_circular_obstacle(impl):
 
 def test_multigrid_stability(impl):
     """TestMultigridStability (fluid_test.go:1470-1547)."""
-    if impl.kind == "gpu":
-        pytest.skip("multigrid V-cycle is out of scope for the CUDA path (SURVEY.md section 8f)")
     f = impl(1.0, 30, 20, 1.0)
     all_fluid(f)
     f.UseMultigrid = True
