@@ -63,7 +63,11 @@
 //   sleeping after a failed poll, a non-blocking test_wait first, one arrive per warp: no change;
 //   issuing the loads of lines rel, rel-1 before the hand-off wait: 0.195; 24 / 32 ring slots,
 //   deeper staging: no change; re-reading the neighbour vectors instead of carrying them (LSU
-//   pipe 79 %); turbulence fused into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2).
+//   pipe 79 %); turbulence fused into the writer (solve + turbulence 3.52 -> 4.20 ms at 16386^2);
+//   8 writer warps instead of 4 (-DRQ_WW=8, 69-72 registers, no spills): 0.184 vs 0.181, with a 16-deep
+//   writer staging ring and 24 slots 0.216; 24 slots alone 0.212 (28 it stays).  RQ_LW = 8 needs a
+//   staging ring deeper than RQ_STG = 8 (a loader warp refills the slot of its next-but-one line) and
+//   is NOT a valid build as is: its result differs.
 #pragma once
 #include "kernels.cuh"
 #include "advect_fused.cuh"
@@ -78,8 +82,12 @@
 #endif
 #define RQ_Q (2 / RQ_SPLIT)         // groups per sweep warp
 #define RQ_SW (RQ_NIT * RQ_SPLIT)   // sweep warps
+#ifndef RQ_LW
 #define RQ_LW 4           // loader warps (line-interleaved)
+#endif
+#ifndef RQ_WW
 #define RQ_WW 4           // writer warps (line-interleaved)
+#endif
 #define RQ_THREADS (32 * (RQ_SW + RQ_LW + RQ_WW))
 #define RQ_WL 512         // columns per slot, whatever TJ is: every lane of a sweep always owns its groups of four cells
 #define RQ_TJ_MAX 464     // multiple of 16; TJ + 2 * RQ_H + 16 <= RQ_WL (16-byte granules for the TMA copies of the mask)
@@ -89,6 +97,9 @@
 #ifndef RQ_WSTG
 #define RQ_WSTG 8         // writer staging ring depth; power of two
 #endif
+static_assert((RQ_STG & (RQ_STG - 1)) == 0 && (RQ_WSTG & (RQ_WSTG - 1)) == 0, "staging ring depths are powers of two");
+static_assert(RQ_STG >= 2 * RQ_LW && RQ_STG % RQ_LW == 0, "a loader warp keeps two of its own lines in flight; shallower rings were measured to give wrong results");
+static_assert(RQ_WSTG % RQ_WW == 0, "a writer warp refills the staging slot of its own next lines");
 // shared memory at TJ = 464: 28 slots * 512 * 9 B (q, -D0, neighbour count) = 126 KB, loader staging
 // 8 * (512*9 + 16) B = 36.1 KB, writer staging 8 * 464 * 9 B = 32.6 KB, hand-off mbarriers 5 KB, wd/s table: 200 KB
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
