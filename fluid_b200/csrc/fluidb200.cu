@@ -612,7 +612,8 @@ static int read_stats(fb_handle *h, unsigned iters)
     return FB_OK;
 }
 
-static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext = 0);
+static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext = 0,
+                                  const float *omega_half_sweeps = nullptr);
 
 // solveMultigridVCycle (fluid.go:560-599): per cycle 3 smoothing sweeps at 1.5, residual ->
 // restriction -> 40 coarse sweeps at 1.6 -> prolongation -> correction, 3 smoothing sweeps at 1.2.
@@ -649,9 +650,21 @@ static int solve_multigrid_vcycle(fb_handle *h, const fb_params *p, float dt, un
     int ib, ie; range(h, 0, ib, ie);
     dim3 rb_grid, rb_block;
     plane_launch(g, ib, ie, rb_grid, rb_block, g.NY / 2 + 1);
-    // three fine-grid sweeps with omega[first .. first+3), max|div| per sweep into d_red[first + s]
+    // FB_SOLVER_REDBLACK_PRESSURE smooths through the fused pressure-form solver, 3 sweeps in one pass over HBM
+    // (2.50 -> 1.85 ms per cycle at 4098^2).  FB_SOLVER_REDBLACK keeps the unfused half sweeps: its fused face-form
+    // kernel is issue-bound and three sweeps of it cost what six k_redblack_half launches do (measured 2.54 vs 2.50 ms).
+    const bool fused_q = p->solver == FB_SOLVER_REDBLACK_PRESSURE;
+    const bool want_stats0 = h->want_stats;
+    h->want_stats = true;                      // the early exit of fluid.go:575 needs max|div| of the third sweep
+    struct Restore { fb_handle *h; bool v; ~Restore() { h->want_stats = v; } } restore{h, want_stats0};
+    // three fine-grid sweeps with omega[first .. first+3); the pre-smoothing's max|div| per sweep lands in d_red[0..2]
     auto smooth = [&](int first) -> int {
         if (exact) return exact_sweeps(h, sp, first, 3);
+        if (fused_q) {
+            float om[6];
+            for (int q = 0; q < 6; q++) om[q] = sp.omega[first];
+            return project_redblack_fused(h, p, dt, 3, false, 0, om);
+        }
         for (int s = 0; s < 3; s++)
             for (int colour = 0; colour < 2; colour++) {
                 k_redblack_half<<<rb_grid, rb_block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], h->f[FB_P], colour,
@@ -695,6 +708,11 @@ static int solve_multigrid_vcycle(fb_handle *h, const fb_params *p, float dt, un
         CKL("k_mg_apply");
         TRY(smooth(3));
     }
+    // fb_get_solve_stats reads the device slots: park the per-cycle values there (the smoothing sweeps used them as scratch)
+    unsigned bits[32];
+    memcpy(bits, h->stats.max_div, sizeof(bits));
+    CK(cudaMemcpyAsync(h->d_red, bits, sizeof(bits), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return FB_OK;
 }
 
@@ -964,12 +982,16 @@ static void rb_geometry(const fb_handle *h, int ib, int ie, int &TJ, int &WL, in
 // makeIncompressible with the red-black ordering, every iteration fused in one pass
 // over HBM (two passes when iters > 8).  Optionally applies addTurbulence to the lines
 // it writes.  Outputs go to fresh planes; roles are swapped afterwards.
-static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext)
+// `omega_half_sweeps` (2 * iters values: red, black, red, ...) replaces the schedule of fluid.go:169-170 --
+// the V-cycle's smoothing sweeps run at a constant relaxation (fluid.go:574, 596).
+static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, unsigned iters, bool fuse_turbulence, int ext,
+                                  const float *omega_half_sweeps)
 {
     TRY(ensure_mask(h));
     SolveParams sp;
     memset(&sp, 0, sizeof(sp));
-    omega_schedule_redblack(p, iters, sp.omega);
+    if (omega_half_sweeps) for (unsigned q = 0; q < 2 * iters && q < 64; q++) sp.omega[q] = omega_half_sweeps[q];
+    else omega_schedule_redblack(p, iters, sp.omega);
     { volatile float dh = h->cfg.density * h->cfg.h; sp.cp = dh / dt; }
     // with slabs `ext` ghost lines are recomputed too, so that the next phase finds them current
     int ib, ie; range(h, ext, ib, ie);

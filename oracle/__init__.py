@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
             "fo_project_redblack": (C.c_float, [P, C.c_uint, C.c_float]),
             "fo_project_redblack_q": (C.c_float, [P, C.c_uint, C.c_float]),
             "fo_project_multigrid_redblack": (None, [P, C.c_uint, C.c_float]),
+            "fo_project_multigrid_redblack_q": (None, [P, C.c_uint, C.c_float]),
             "fo_project_redblack_sched": (C.c_float, [P, C.c_void_p, C.c_uint, C.c_float]),
         }
         for name, (res, args) in sig.items():
@@ -232,6 +233,8 @@ class OracleFluid:
     # ---- hot path
     def _project_rb(self, iters, dt):
         if self.UseMultigrid and self.MultigridLevels > 1:
+            if self.Solver == SOLVER_REDBLACK_PRESSURE:
+                return self._l.fo_project_multigrid_redblack_q(self._f, iters, dt)
             return self._l.fo_project_multigrid_redblack(self._f, iters, dt)
         fn = self._l.fo_project_redblack_q if self.Solver == SOLVER_REDBLACK_PRESSURE else self._l.fo_project_redblack
         return fn(self._f, iters, dt)

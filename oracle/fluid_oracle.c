@@ -391,26 +391,40 @@ static void apply_pressure_correction(fo_fluid *f, const float *correction, floa
 }
 
 static float redblack_half(fo_fluid *f, float relaxation, float cp, int colour);
+static void redblack_q_pass(fo_fluid *f, const float *omega, unsigned iters, float cp);
 
-/* One fine-grid smoothing sweep: pressureJacobiIteration (fluid.go:188-234), or with redblack its
- * two half sweeps (max |div| over both). */
-static float mg_smooth(fo_fluid *f, float relaxation, float cp, int redblack)
+/* Three fine-grid smoothing sweeps at one relaxation; returns max |div| of the third.
+ * mode 0: pressureJacobiIteration (fluid.go:188-234), the reference.  NOT in the reference: mode 1, each
+ * sweep as a red and a black half sweep; mode 2, the same three red-black sweeps in pressure form as one
+ * pass (the arithmetic of rbq_fused.cuh, see redblack_q_pass). */
+static float mg_smooth3(fo_fluid *f, float relaxation, float cp, int mode)
 {
-    if (!redblack) return fo_pressure_iteration(f, relaxation, cp);
-    float a = redblack_half(f, relaxation, cp, 0);
-    float b = redblack_half(f, relaxation, cp, 1);
-    return a > b ? a : b;
+    float maxDiv = 0.0f;
+    if (mode == 2) {
+        const float om[6] = { relaxation, relaxation, relaxation, relaxation, relaxation, relaxation };
+        redblack_q_pass(f, om, 3, cp);
+        return f->last_maxdiv;
+    }
+    for (unsigned s = 0; s < 3; s++) {
+        if (mode == 0) maxDiv = fo_pressure_iteration(f, relaxation, cp);
+        else {
+            float a = redblack_half(f, relaxation, cp, 0);
+            float b = redblack_half(f, relaxation, cp, 1);
+            maxDiv = a > b ? a : b;
+        }
+    }
+    return maxDiv;
 }
 
-static void solve_multigrid_vcycle(fo_fluid *f, unsigned numIters, float dt, int redblack)
+static void solve_multigrid_vcycle(fo_fluid *f, unsigned numIters, float dt, int mode)
 {
+    const int redblack = mode != 0;
     float cp = f->density * f->h / dt;
     const float tolerance = 1e-5f;
     f->last_iters = 0;
     f->last_maxdiv = 0.0f;
     for (unsigned iter = 0; iter < numIters; iter++) {
-        float maxDiv = 0.0f;
-        for (unsigned s = 0; s < 3; s++) maxDiv = mg_smooth(f, 1.5f, cp, redblack);
+        float maxDiv = mg_smooth3(f, 1.5f, cp, mode);
         f->last_iters = (int)iter + 1;      /* cycles entered */
         f->last_maxdiv = maxDiv;            /* the value fluid.go:575 tests */
         if (maxDiv < tolerance) break;
@@ -419,7 +433,9 @@ static void solve_multigrid_vcycle(fo_fluid *f, unsigned numIters, float dt, int
         float *coarseCorr = solve_coarse_grid(f, coarseRHS, redblack);
         float *corr = prolongate_correction(f, coarseCorr);
         apply_pressure_correction(f, corr, cp);
-        for (unsigned s = 0; s < 3; s++) mg_smooth(f, 1.2f, cp, redblack);
+        mg_smooth3(f, 1.2f, cp, mode);
+        f->last_iters = (int)iter + 1;
+        f->last_maxdiv = maxDiv;
         free(residual); free(coarseRHS); free(coarseCorr); free(corr);
     }
 }
@@ -430,6 +446,14 @@ void fo_project_multigrid_redblack(fo_fluid *f, unsigned iters, float dt)
     fo_copy_border(f, f->newU, f->U);
     fo_copy_border(f, f->newV, f->V);
     solve_multigrid_vcycle(f, iters, dt, 1);
+}
+
+/* NOT in the reference: the same with the smoothing sweeps in pressure form (FB_SOLVER_REDBLACK_PRESSURE). */
+void fo_project_multigrid_redblack_q(fo_fluid *f, unsigned iters, float dt)
+{
+    fo_copy_border(f, f->newU, f->U);
+    fo_copy_border(f, f->newV, f->V);
+    solve_multigrid_vcycle(f, iters, dt, 2);
 }
 
 /* ---- makeIncompressible (fluid.go:144-155) ------------------------------ */

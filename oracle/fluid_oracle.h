@@ -132,6 +132,9 @@ float fo_project_redblack_q(fo_fluid *f, unsigned iters, float dt);
  * fine-grid smoothing sweeps and the 40 coarse ones -- in red-black order; residual, restriction,
  * prolongation and correction as in the reference.  Checks the CUDA fast-mode V-cycle bit for bit. */
 void fo_project_multigrid_redblack(fo_fluid *f, unsigned iters, float dt);
+/* ... and with each block of three smoothing sweeps run as ONE pressure-form pass (fo_project_redblack_q's
+ * arithmetic), which is what FB_SOLVER_REDBLACK_PRESSURE does. */
+void fo_project_multigrid_redblack_q(fo_fluid *f, unsigned iters, float dt);
 /* Same with an explicit omega per HALF sweep: omega[2k] red, omega[2k+1] black. */
 float fo_project_redblack_sched(fo_fluid *f, const float *omega, unsigned iters, float dt);
 
