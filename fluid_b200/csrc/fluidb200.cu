@@ -1023,15 +1023,16 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             const int tj = cdiv(cdiv(h->g.NY, ns), 16) * 16;
             if (tj > RQ_TJ_MAX || tj < 16) continue;
             const int nstr = cdiv(h->g.NY, tj);
-            int nch = h->nsm / nstr; if (nch < 1) nch = 1;
+            const int slots = h->nsm * RQ_MINB;                          // CTAs resident at once
+            int nch = slots / nstr; if (nch < 1) nch = 1;
             const int max_chunks = cdiv(lines, 48);
             if (nch > max_chunks) nch = max_chunks;
             if (nch < 1) nch = 1;
             const int ch = cdiv(lines, nch);
             nch = cdiv(lines, ch);
             const int ctas = nstr * nch;
-            const int waves = cdiv(ctas, h->nsm);
-            const double util = (double)ctas / (waves * h->nsm);
+            const int waves = cdiv(ctas, slots);
+            const double util = (double)ctas / (waves * slots);
             const double overhead = ((double)(tj + 2 * RQ_H + 16) / tj) * ((double)(ch + 2 * RQ_H) / ch);
             const double score = util / overhead / waves;
             if (score > best) { best = score; TJ = tj; nstrips = nstr; chunk = ch; nchunks = nch; }

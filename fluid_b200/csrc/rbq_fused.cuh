@@ -80,7 +80,15 @@
 #ifndef RQ_SPLIT
 #define RQ_SPLIT 2        // warps per stage (1 or 2): a line is 2 groups of 128 same-parity cells, 4 per lane
 #endif
-#define RQ_Q (2 / RQ_SPLIT)         // groups per sweep warp
+#ifndef RQ_WL
+#define RQ_WL 512         // columns per slot, whatever TJ is: every lane of a sweep always owns its groups of four cells
+#endif
+#define RQ_G (RQ_WL / 256)          // groups of 128 same-parity cells in a line (4 per lane)
+#define RQ_Q (RQ_G / RQ_SPLIT)      // groups per sweep warp
+#ifndef RQ_MINB
+#define RQ_MINB 1         // CTAs per SM the kernel is compiled for (experiment: RQ_WL = 256, RQ_SPLIT = 1, RQ_MINB = 2)
+#endif
+static_assert(RQ_WL % 256 == 0 && RQ_G >= RQ_SPLIT && RQ_G % RQ_SPLIT == 0, "a sweep warp owns whole groups of 128 same-parity cells");
 #define RQ_SW (RQ_NIT * RQ_SPLIT)   // sweep warps
 #ifndef RQ_LW
 #define RQ_LW 4           // loader warps (line-interleaved)
@@ -89,8 +97,7 @@
 #define RQ_WW 4           // writer warps (line-interleaved)
 #endif
 #define RQ_THREADS (32 * (RQ_SW + RQ_LW + RQ_WW))
-#define RQ_WL 512         // columns per slot, whatever TJ is: every lane of a sweep always owns its groups of four cells
-#define RQ_TJ_MAX 464     // multiple of 16; TJ + 2 * RQ_H + 16 <= RQ_WL (16-byte granules for the TMA copies of the mask)
+#define RQ_TJ_MAX (RQ_WL - 48)   // 464: multiple of 16; TJ + 2 * RQ_H + 16 <= RQ_WL (16-byte granules for the TMA copies of the mask)
 #ifndef RQ_STG
 #define RQ_STG 8          // staging ring depth (lines in flight through TMA); power of two
 #endif
@@ -368,7 +375,7 @@ __device__ __forceinline__ void rq_pair_stage(RQStage &S)
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
+__global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int WL = RQ_WL, WQ = WL >> 1, ROW = WL;            // elements per slot in one plane
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
             const int e_slot = sl * ROW;
 #pragma unroll
-            for (int cg = 0; cg < 4; cg++) {
+            for (int cg = 0; cg < RQ_WL / 128; cg++) {
                 const int ld = lane + 32 * cg;
                 const int j = jr0 + 4 * ld;
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -575,7 +582,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_rbq_fused(const RBQ P)
             const int e_line = sl * ROW, e_linem = (sl == 0 ? RQ_NL - 1 : sl - 1) * ROW;
             const bool line_first = (r == 0);
 #pragma unroll 2
-            for (int cg = 0; cg < 4; cg++) {
+            for (int cg = 0; cg < RQ_WL / 128; cg++) {
                 const int st = lane + 32 * cg;
                 const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
                 if (st >= (P.TJ >> 2) || w_j >= NY || (P.xflags & 2)) continue;

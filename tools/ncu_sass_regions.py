@@ -10,7 +10,12 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 col = {n: i for i, n in enumerate(hdr)}
 stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
-body = [r for r in rows[hi + 1:] if len(r) > col["Instructions Executed"]]
+body = []
+for r in rows[hi + 1:]:          # newer ncu prints the table twice (per view): keep the first
+    if r and r[0] in ("Address", "Kernel Name"):
+        break
+    if len(r) > col["Instructions Executed"]:
+        body.append(r)
 tot_i = sum(int(r[col["Instructions Executed"]]) for r in body)
 tot_s = sum(int(r[col["# Samples"]]) for r in body)
 print("instructions", tot_i, "samples", tot_s)
