@@ -81,3 +81,29 @@ def test_emulated_kernels_reproduce_the_oracle_cycle(oracle_mod, emul, width, he
     for name in ("U", "V", "p"):
         assert_bit_exact(f"{width}x{height}/solver{solver}:{name}", got.get(name), want.get(name))
     assert np.isfinite(want.U).all() and np.isfinite(want.p).all()
+
+
+def test_emulated_kernels_all_small_sizes(oracle_mod, emul):
+    """Every NumX, NumY parity combination and the degenerate coarse grids (cNX or cNY <= 2): one cycle, both orders."""
+    dt = np.float32(1.0 / 60.0)
+    checked = 0
+    for width in range(1, 12):
+        for height in (1, 2, 3, 4, 7, 10, 33):
+            for solver in (0, 1):
+                want = scene(oracle_mod, width, height, 100 * width + height, solver, (width + height) % 2 == 0)
+                got = scene(oracle_mod, width, height, 100 * width + height, solver, (width + height) % 2 == 0)
+                want.makeIncompressible(1, dt)
+                cp = np.float32(np.float32(got.density) * np.float32(got.h)) / dt
+                for _s in range(3):
+                    md = got.pressureIteration(1.5, cp) if solver == 0 else got.redblackIteration(1.5, dt)
+                if md >= 1e-5:
+                    emul.mg_emul_correct(got.U.ctypes.data, got.V.ctypes.data, got.S.ctypes.data, got.p.ctypes.data,
+                                         got.NumX, got.NumY, cp, 1 if solver == 0 else 0)
+                    for _s in range(3):
+                        got.pressureIteration(1.2, cp) if solver == 0 else got.redblackIteration(1.2, dt)
+                for name in ("U", "V", "p"):
+                    assert_bit_exact(f"{width}x{height}/solver{solver}:{name}", got.get(name), want.get(name))
+                checked += 1
+                want.close()
+                got.close()
+    assert checked == 11 * 7 * 2
