@@ -13,6 +13,11 @@
 # with a 56-slot ring (wl256deep).  Halo overhead 1.30 instead of 1.26.  The default build (RQ_WL=512) is unchanged:
 # its SASS was compared instruction for instruction when these knobs were added.
 #
+# Third idea (needs code, not a macro): the loader's and the writer's four warps are line-interleaved, so a line spends
+# four line periods in each role.  With all four warps of a role on ONE line (a quarter of the columns each, hand-off
+# count 128 like the two warps of a sweep stage) that is one period each: ~6 line periods less residency, the same
+# as 6 more slots, for no shared memory.
+#
 #   here:    tools/r02_rbq_ring.sh build
 #   gpurun:  tools/r02_rbq_ring.sh run        (prints ms for 1 and 8 iterations and a hash of U, V, p per variant:
 #                                              equal hashes <=> bit-identical results; then run pytest -m gpu with
