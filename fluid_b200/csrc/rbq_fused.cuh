@@ -97,6 +97,19 @@ static_assert(RQ_WL % 256 == 0 && RQ_G >= RQ_SPLIT && RQ_G % RQ_SPLIT == 0, "a s
 #define RQ_WW 4           // writer warps (line-interleaved)
 #endif
 #define RQ_THREADS (32 * (RQ_SW + RQ_LW + RQ_WW))
+#ifndef RQ_RING_LOG2
+#define RQ_RING_LOG2 (RQ_NL < 32 ? 6 : 7)
+#endif
+#define RQ_RING (1 << RQ_RING_LOG2)       // hand-off mbarriers per role; > 2 * RQ_NL (see "hand-offs" below)
+// Experiments (tools/r02_rbq_ring.sh): RQ_LSPLIT / RQ_WSPLIT warps of the loader / writer share ONE line (each takes
+// its part of the column groups) instead of taking whole lines in turn; a line then stays RQ_LW / RQ_LSPLIT line
+// periods in the role instead of RQ_LW.  1 = line-interleaved (the measured default).
+#ifndef RQ_LSPLIT
+#define RQ_LSPLIT 1
+#endif
+#ifndef RQ_WSPLIT
+#define RQ_WSPLIT 1
+#endif
 #define RQ_TJ_MAX (RQ_WL - 48)   // 464: multiple of 16; TJ + 2 * RQ_H + 16 <= RQ_WL (16-byte granules for the TMA copies of the mask)
 #ifndef RQ_STG
 #define RQ_STG 8          // staging ring depth (lines in flight through TMA); power of two
@@ -107,6 +120,9 @@ static_assert(RQ_WL % 256 == 0 && RQ_G >= RQ_SPLIT && RQ_G % RQ_SPLIT == 0, "a s
 static_assert((RQ_STG & (RQ_STG - 1)) == 0 && (RQ_WSTG & (RQ_WSTG - 1)) == 0, "staging ring depths are powers of two");
 static_assert(RQ_STG >= 2 * RQ_LW && RQ_STG % RQ_LW == 0, "a loader warp keeps two of its own lines in flight; shallower rings were measured to give wrong results");
 static_assert(RQ_WSTG % RQ_WW == 0, "a writer warp refills the staging slot of its own next lines");
+static_assert((RQ_RING & (RQ_RING - 1)) == 0 && RQ_RING > 2 * RQ_NL, "a parity wait must refer to the current or the preceding phase");
+static_assert(RQ_LW % RQ_LSPLIT == 0 && (RQ_WL / 128) % RQ_LSPLIT == 0 && RQ_STG % (RQ_LW / RQ_LSPLIT) == 0, "loader split");
+static_assert(RQ_WW % RQ_WSPLIT == 0 && (RQ_WL / 128) % RQ_WSPLIT == 0 && RQ_WSTG % (RQ_WW / RQ_WSPLIT) == 0, "writer split");
 // shared memory at TJ = 464: 28 slots * 512 * 9 B (q, -D0, neighbour count) = 126 KB, loader staging
 // 8 * (512*9 + 16) B = 36.1 KB, writer staging 8 * 464 * 9 B = 32.6 KB, hand-off mbarriers 5 KB, wd/s table: 200 KB
 __host__ __device__ __forceinline__ size_t rq_stage_bytes(int WL) { return (size_t)WL * 9 + 16; }
@@ -114,7 +130,7 @@ __host__ __device__ __forceinline__ size_t rq_wstage_bytes(int TJ) { return (siz
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int WL, int TJ)
 {
     return (size_t)RQ_NL * WL * 9 + RQ_STG * rq_stage_bytes(WL) + RQ_WSTG * rq_wstage_bytes(TJ) + 8 * (RQ_STG + RQ_WSTG) +
-           8 * (RQ_NIT + 2) * 64 + 16 * 8 * 4 + 64;
+           8 * (RQ_NIT + 2) * RQ_RING + 16 * 8 * 4 + 64;
 }
 
 struct RBQ {
@@ -175,7 +191,6 @@ __device__ __forceinline__ void rq_tma_load(unsigned dst, const void *src, unsig
 // that own the line arrives, every lane of a consumer polls with try_wait.  Each role arrives for EVERY line
 // 0 .. nproc, and no role can be more than RQ_NL lines ahead of another (the loader waits for the slot), so
 // with RQ_RING > 2 * RQ_NL a parity wait always refers to the current or the immediately preceding phase.
-#define RQ_RING 64
 #define RQ_ROLES (RQ_NIT + 2)
 #define RQ_WROLE (RQ_NIT + 1)
 // Bounded waits: a pipeline that stops making progress must never hang the GPU.  After ~2^21 failed polls
@@ -212,7 +227,7 @@ __device__ __forceinline__ void rq_wait_a(unsigned bar, unsigned parity, int tag
 // line / step `line` of the role whose ring starts at `ring`
 __device__ __forceinline__ void rq_wait_line(unsigned ring, int line, int tag)
 {
-    rq_wait_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)), (unsigned)(line >> 6) & 1u, tag | line);
+    rq_wait_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)), (unsigned)(line >> RQ_RING_LOG2) & 1u, tag | line);
 }
 __device__ __forceinline__ void rq_done_line(unsigned ring, int line)
 {
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
     // arrivals per phase: every lane of the warp(s) that own the line / step
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, (role == 0 || role == RQ_WROLE) ? 32 : 32 * RQ_SPLIT);
+        rq_mbar_init(bars + k, role == 0 ? 32 * RQ_LSPLIT : (role == RQ_WROLE ? 32 * RQ_WSPLIT : 32 * RQ_SPLIT));
     }
     if (tid >= 32 && tid < 32 + RQ_STG) rq_mbar_init(full + tid - 32, 1);
     if (tid >= 64 && tid < 64 + RQ_WSTG) rq_mbar_init(wfull + tid - 64, 1);
@@ -450,6 +465,16 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
         // Loader warp k takes lines k, k + RQ_LW, ...: a lane owns 4 columns in each of the 4 groups of 128, so a
         // warp has RQ_LW line periods for its line and the groups are independent work.
         const int lw = warp - RQ_SW;
+        constexpr int LGRP = RQ_LW / RQ_LSPLIT;               // lines in flight in the loader
+        constexpr int LCG = (RQ_WL / 128) / RQ_LSPLIT;        // column groups of a line per warp
+#if RQ_LSPLIT > 1
+        const int lgrp = lw / RQ_LSPLIT, lpart = lw % RQ_LSPLIT;
+        const bool l_issuer = lane == 0 && lpart == 0;        // the one lane that feeds this line's TMA slot
+#else
+        const int lgrp = lw;
+        constexpr int lpart = 0;
+#define l_issuer (lane == 0)
+#endif
         // only interior lines inside this rank's slab hold updatable cells (the mask's count bits are
         // zero on the ring and in solids); line e1 is loaded but never swept
         const int live_lo = max(1, g.i_alloc0) - e0;
@@ -481,10 +506,10 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
                 rq_mbar_arrive(full + k);
             }
         };
-        if (lane == 0)
-            for (int line = lw; line < RQ_STG && line <= nproc; line += RQ_LW) stage_line(line);
-        int sl = lw;                                         // slot of line rel
-        for (int rel = lw; rel <= nproc; rel += RQ_LW) {
+        if (l_issuer)
+            for (int line = lgrp; line < RQ_STG && line <= nproc; line += LGRP) stage_line(line);
+        int sl = lgrp;                                       // slot of line rel
+        for (int rel = lgrp; rel <= nproc; rel += LGRP) {
             // slot(rel) last held line y-1 with y = rel - NL + 1.  Its readers: the stages up to the last one's step y
             // (which writes line y-1 for the last time) and, for owned lines, the writer at lines y-1 and y.
             const int y = rel - RQ_NL + 1;
@@ -501,7 +526,8 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
             const int e_slot = sl * ROW;
 #pragma unroll
-            for (int cg = 0; cg < RQ_WL / 128; cg++) {
+            for (int cgi = 0; cgi < LCG; cgi++) {
+                const int cg = lpart * LCG + cgi;
                 const int ld = lane + 32 * cg;
                 const int j = jr0 + 4 * ld;
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -532,12 +558,15 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             }
             rq_done_line(ring_ld, rel);
             __syncwarp();                                    // every lane is done with staging slot st0
-            if (lane == 0 && rel + RQ_STG <= nproc) {
+            if (l_issuer && rel + RQ_STG <= nproc) {
+#if RQ_LSPLIT > 1
+                rq_wait_line(ring_ld, rel, 36 << 20);                         // the other warps of this line
+#endif
                 // the slot also was the "line above" of line rel-1, which another loader warp handles
                 if (rel >= 1) rq_wait_line(ring_ld, rel - 1, 35 << 20);
                 stage_line(rel + RQ_STG);
             }
-            sl += RQ_LW; if (sl >= RQ_NL) sl -= RQ_NL;
+            sl += LGRP; if (sl >= RQ_NL) sl -= RQ_NL;
         }
     } else if (warp < RQ_SW + RQ_LW + RQ_WW) {
         // ================= writer: owned lines -> U, V, p =================
@@ -545,10 +574,20 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
         // mask of a line come from the writer's own TMA staging ring (second producer below): re-read through
         // registers they missed L2 two times in three and every line paid a DRAM round trip.
         const int ww = warp - RQ_SW - RQ_LW;
+        constexpr int WGRP = RQ_WW / RQ_WSPLIT;               // lines in flight in the writer
+        constexpr int WCG = (RQ_WL / 128) / RQ_WSPLIT;
+#if RQ_WSPLIT > 1
+        const int wgrp = ww / RQ_WSPLIT, wpart = ww % RQ_WSPLIT;
+        const bool w_issuer = lane == 0 && wpart == 0;
+#else
+        const int wgrp = ww;
+        constexpr int wpart = 0;
+#define w_issuer (lane == 0)
+#endif
         const unsigned b_wfull = rq_s32(wfull), ring_last = rq_s32(bars + nit * RQ_RING);
         // only owned lines are written, but the hand-off phases count every line: arrive for the halo lines first
-        for (int rel = ww; rel < own0; rel += RQ_WW) rq_done_line(ring_wr, rel);
-        int sl = (own0 + ww) % RQ_NL;
+        for (int rel = wgrp; rel < own0; rel += WGRP) rq_done_line(ring_wr, rel);
+        int sl = (own0 + wgrp) % RQ_NL;
         const bool turb = P.turb > 0.0f;
         const float cp = P.cp;
         const int oV = 4 * P.TJ;
@@ -572,9 +611,9 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
                 rq_mbar_arrive(wfull + k);
             }
         };
-        if (lane == 0)
-            for (int n = ww; n < RQ_WSTG && n < i1c - i0c; n += RQ_WW) stage_line(n);
-        for (int n = ww; n < i1c - i0c; n += RQ_WW) {
+        if (w_issuer)
+            for (int n = wgrp; n < RQ_WSTG && n < i1c - i0c; n += WGRP) stage_line(n);
+        for (int n = wgrp; n < i1c - i0c; n += WGRP) {
             const int r = i0c + n, rel = r - e0;
             rq_wait_line(ring_last, rel + 1, nst << 20);                // the last iteration has finished its step rel+1: line r is final
             const int ws = n & (RQ_WSTG - 1);
@@ -582,7 +621,8 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             const int e_line = sl * ROW, e_linem = (sl == 0 ? RQ_NL - 1 : sl - 1) * ROW;
             const bool line_first = (r == 0);
 #pragma unroll 2
-            for (int cg = 0; cg < RQ_WL / 128; cg++) {
+            for (int cgi = 0; cgi < WCG; cgi++) {
+                const int cg = wpart * WCG + cgi;
                 const int st = lane + 32 * cg;
                 const int w_lj = RQ_H + 4 * st, w_j = jr0 + w_lj;
                 if (st >= (P.TJ >> 2) || w_j >= NY || (P.xflags & 2)) continue;
@@ -645,8 +685,17 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             }
             rq_done_line(ring_wr, rel);                               // the slots of line r are free
             __syncwarp();
+#if RQ_WSPLIT > 1
+            if (w_issuer && n + RQ_WSTG < i1c - i0c) {
+                rq_wait_line(ring_wr, rel, 37 << 20);                         // the other warps of this line
+                stage_line(n + RQ_WSTG);
+            }
+#else
             if (lane == 0 && n + RQ_WSTG < i1c - i0c) stage_line(n + RQ_WSTG);
-            sl += RQ_WW; if (sl >= RQ_NL) sl -= RQ_NL;
+#endif
+            sl += WGRP; if (sl >= RQ_NL) sl -= RQ_NL;
         }
     }
 }
+#undef l_issuer
+#undef w_issuer

@@ -13,10 +13,11 @@
 # with a 56-slot ring (wl256deep).  Halo overhead 1.30 instead of 1.26.  The default build (RQ_WL=512) is unchanged:
 # its SASS was compared instruction for instruction when these knobs were added.
 #
-# Third idea (needs code, not a macro): the loader's and the writer's four warps are line-interleaved, so a line spends
-# four line periods in each role.  With all four warps of a role on ONE line (a quarter of the columns each, hand-off
-# count 128 like the two warps of a sweep stage) that is one period each: ~6 line periods less residency, the same
-# as 6 more slots, for no shared memory.
+# Third idea: the loader's and the writer's four warps are line-interleaved, so a line spends four line periods in each
+# role.  With RQ_LSPLIT / RQ_WSPLIT = 2 or 4 warps of a role on ONE line (half / a quarter of the column groups each,
+# hand-off count 32 x split like the two warps of a sweep stage) that is two / one period each: up to ~6 line periods
+# less residency, the same as 6 more slots, for no shared memory (but 2-4x the hand-off polls in those roles).
+# 32 and more slots switch the hand-off rings to 128 mbarriers per role (RQ_RING > 2 * RQ_NL).
 #
 #   here:    tools/r02_rbq_ring.sh build
 #   gpurun:  tools/r02_rbq_ring.sh run        (prints ms for 1 and 8 iterations and a hash of U, V, p per variant:
@@ -32,9 +33,12 @@ build)
                     nl36w4 "-DRQ_NL=36 -DRQ_WSTG=4" \
                     nl28w4 "-DRQ_WSTG=4" \
                     wl256x2 "-DRQ_WL=256 -DRQ_SPLIT=1 -DRQ_MINB=2" \
-                    wl256deep "-DRQ_WL=256 -DRQ_SPLIT=1 -DRQ_NL=56" ;;
+                    wl256deep "-DRQ_WL=256 -DRQ_SPLIT=1 -DRQ_NL=56" \
+                    ls2ws2 "-DRQ_LSPLIT=2 -DRQ_WSPLIT=2" \
+                    ls4ws4 "-DRQ_LSPLIT=4 -DRQ_WSPLIT=4" \
+                    nl32w4s2 "-DRQ_NL=32 -DRQ_WSTG=4 -DRQ_LSPLIT=2 -DRQ_WSPLIT=2" ;;
 run)
-  for v in base nl28w4 nl32w4 nl34w4 nl36w4 wl256x2 wl256deep; do
+  for v in base nl28w4 nl32w4 nl34w4 nl36w4 wl256x2 wl256deep ls2ws2 ls4ws4 nl32w4s2; do
     echo -n "$v: "; FLUIDB200_LIB=$PWD/tools/variants/lib_$v.so timeout 40 python tools/rbq_iters.py 1 8 2>&1 | tail -1
   done ;;
 *) echo "usage: $0 build|run"; exit 2 ;;
