@@ -1,6 +1,8 @@
 """ctypes binding of libfluidb200.so -- the same entry points a cgo binding uses
-(include/fluidb200.h).  There is no CPU fallback: if the CUDA library is missing
-or does not load, importing this module raises."""
+(include/fluidb200.h).  The library is opened on the FIRST use of ``lib`` (so that the
+pure-Python helpers -- presets, edit lists, slab planning -- import on a checkout
+without it); there is no CPU fallback: if it is missing or does not load, that first
+use raises ImportError."""
 from __future__ import annotations
 
 import ctypes as C
@@ -111,7 +113,19 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     return lib
 
 
-lib = load()
+class _LazyLib:
+    """``lib.fb_xxx`` opens the library on first attribute access and then gets out of the way."""
+    _cdll = None
+
+    def __getattr__(self, name):
+        if _LazyLib._cdll is None:
+            _LazyLib._cdll = load()
+        fn = getattr(_LazyLib._cdll, name)
+        setattr(self, name, fn)
+        return fn
+
+
+lib = _LazyLib()
 
 
 class FluidError(RuntimeError):

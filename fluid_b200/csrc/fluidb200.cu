@@ -5,6 +5,7 @@
 #include "advect_fused.cuh"
 #include "rb_fused.cuh"
 #include "rbq_fused.cuh"
+#include "rbq_stream.cuh"
 #include "multigrid.cuh"
 
 #include <cmath>
@@ -1014,7 +1015,37 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         }
     }
     const bool pressure_form = p->solver == FB_SOLVER_REDBLACK_PRESSURE;
-    if (pressure_form) {
+    static const bool rbq_ring = getenv("FLUIDB200_RBQ_RING") != nullptr;       // A/B: the shared-memory ring pipeline of round 1
+    if (pressure_form && !rbq_ring) {
+        // k_rbq_stream: one warp (= CTA) per strip x chunk; all warps resident in ONE wave, least halo recomputation
+        const int lines = ie - ib;
+        double best = -1.0;
+        const int s_min = cdiv(h->g.NY, RS_TJ_MAX);
+        for (int ns = s_min; ns <= s_min + 8; ns++) {
+            const int tj = cdiv(cdiv(h->g.NY, ns), 16) * 16;
+            if (tj > RS_TJ_MAX || tj < 16) continue;
+            const int nstr = cdiv(h->g.NY, tj);
+            const int slots = h->nsm * RS_CPS;
+            int nch = slots / nstr; if (nch < 1) nch = 1;
+            const int max_chunks = cdiv(lines, 32);
+            if (nch > max_chunks) nch = max_chunks;
+            if (nch < 1) nch = 1;
+            const int ch = cdiv(lines, nch);
+            nch = cdiv(lines, ch);
+            const int ctas = nstr * nch;
+            const int waves = cdiv(ctas, slots);
+            const double util = (double)ctas / (waves * slots);
+            const double overhead = ((double)RS_W / tj) * ((double)(ch + 2 * RS_H) / ch);
+            const double score = util / overhead / waves;
+            if (score > best) { best = score; TJ = tj; nstrips = nstr; chunk = ch; nchunks = nch; }
+        }
+        WL = RS_W;
+        if (!h->rbq_attr_set) {
+            CK(cudaFuncSetAttribute(k_rbq_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+            CK(cudaFuncSetAttribute(k_rbq_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+            h->rbq_attr_set = true;
+        }
+    } else if (pressure_form) {
         // pick strips x chunks: as many of the SMs as possible in ONE wave, least halo recomputation
         const int lines = ie - ib;
         double best = -1.0;
@@ -1056,7 +1087,11 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         a.Pin = h->p_zero ? nullptr : h->f[FB_P];
         a.mask = h->mask;
         a.Uo = Uo; a.Vo = Vo; a.Po = Po;
-        for (unsigned q = 0; q < 2 * k; q++) { volatile float w = sp.omega[2 * done + q] * p->pressure_damping; a.wd[q] = w; }
+        for (unsigned q = 0; q < 2 * k; q++) {
+            volatile float w = sp.omega[2 * done + q] * p->pressure_damping;
+            volatile float w4 = w * 0.25f;
+            a.wd[q] = w; a.nwd[q] = -w; a.c4[q] = w4;
+        }
         a.cp = sp.cp;
         a.nstages = (int)(2 * k); a.stage0 = (int)(2 * done);
         a.TJ = TJ; a.WL = WL; a.chunk = chunk; a.ib = ib; a.ie = ie;
@@ -1069,9 +1104,16 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             a.noiseU = nU; a.noiseV = nV; a.turb = ts;
         }
         const size_t smem_q = rq_smem_bytes(WL, TJ);   // planes + TMA staging ring + mbarriers + progress counters
-        if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
-        else k_rbq_fused<false><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
-        CKL("k_rbq_fused");
+        if (!rbq_ring) {
+            // fewer than 8 iterations: the trailing stages run with wd = 0 (memset above), which leaves q as it is
+            if (h->want_stats) k_rbq_stream<true><<<dim3(nstrips, nchunks, 1), 64, RS_SMEM, h->stream>>>(a);
+            else k_rbq_stream<false><<<dim3(nstrips, nchunks, 1), 64, RS_SMEM, h->stream>>>(a);
+            CKL("k_rbq_stream");
+        } else {
+            if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
+            else k_rbq_fused<false><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
+            CKL("k_rbq_fused");
+        }
         give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]); give_plane(h, h->f[FB_P]);
         h->f[FB_U] = Uo; h->f[FB_V] = Vo; h->f[FB_P] = Po;
         h->p_zero = false;
@@ -1580,6 +1622,8 @@ extern "C" int fb_view(fb_handle *h, int32_t kind, float *out, float *min_value,
     if (!h) return FB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     const Grid &g = h->g;
+    // the pipelined forms own the reduction slots and the view scratch until fb_view_end / fb_render_end
+    if (h->view_in_flight) return fail(h, FB_ERR_INVALID, "fb_view: a pipelined view is in flight (fb_view_end / fb_render_end first)");
     int ib, ie; range(h, 0, ib, ie);
     dim3 grid, block; plane_launch(g, ib, ie, grid, block);
     // sentinels of pressure.go:6-7 / fluid.go:810-811

@@ -140,6 +140,7 @@ struct RBQ {
     const unsigned char *mask;
     float *Uo, *Vo, *Po;
     float wd[16];                // omega*damping per half sweep
+    float nwd[16], c4[16];       // -wd and wd/4 (k_rbq_stream takes them from the constant bank)
     float cp;
     int nstages, stage0;
     int TJ, WL, chunk, ib, ie;

@@ -125,13 +125,18 @@ class SlabFluid:
     ``Fluid`` (step / edit / get / MaxDivergence / timers)."""
 
     EXCHANGED = (L.U, L.V, L.M)
+    # every exported knob of Fluid is forwarded to the slab's handle; anything else that looks like one is rejected
+    KNOBS = ("UseBFECC", "Confinement", "TurbulenceStrength", "PressureDamping", "SmokeAdvection", "NumIters", "Solver",
+             "ViscosityDiffusion", "UseMultigrid", "MultigridLevels", "Relaxation")
 
     def __init__(self, density, width, height, h, *, solver=L.SOLVER_REDBLACK_PRESSURE, device=0, rank=0,
-                 nranks=1, ghost=48, reach=6, transport="peer", connect=True):
+                 nranks=1, ghost=None, reach=6, transport="peer", connect=True):
         import torch
         import torch.distributed as dist
         if solver == L.SOLVER_EXACT:
             raise ValueError("the lexicographic solver does not decompose into slabs; use a red-black solver")
+        if ghost is None:            # enough for any step fb_step_local accepts at this reach (BFECC + confinement)
+            ghost = required_ghost(reach, True, True)
         self.torch, self.dist = torch, dist
         self.rank, self.nranks, self.device = rank, nranks, device
         self.reach = reach
@@ -171,15 +176,15 @@ class SlabFluid:
 
     # knobs are forwarded to the slab's Fluid
     def __getattr__(self, name):
-        if name in ("UseBFECC", "Confinement", "TurbulenceStrength", "PressureDamping", "SmokeAdvection", "NumIters",
-                    "Solver"):
+        if name in SlabFluid.KNOBS:
             return getattr(self.f, name)
         raise AttributeError(name)
 
     def __setattr__(self, name, value):
-        if name in ("UseBFECC", "Confinement", "TurbulenceStrength", "PressureDamping", "SmokeAdvection", "NumIters",
-                    "Solver"):
-            setattr(self.f, name, value)
+        if name in SlabFluid.KNOBS:
+            setattr(self.f, name, value)       # unsupported combinations (viscosity, multigrid on slabs) fail in fb_step_local
+        elif name[:1].isupper() and name not in ("NumX", "NumY"):
+            raise AttributeError(f"SlabFluid has no knob {name!r}")
         else:
             object.__setattr__(self, name, value)
 
@@ -301,7 +306,7 @@ class LocalSlabGroup:
     used to check slab-vs-single-domain bit identity on a single-GPU box."""
 
     def __init__(self, density, width, height, h, nslabs, *, solver=L.SOLVER_REDBLACK_PRESSURE, devices=None,
-                 ghost=48, reach=6, transport="peer"):
+                 ghost=None, reach=6, transport="peer"):
         devices = devices or [0] * nslabs
         self.slabs = [SlabFluid(density, width, height, h, solver=solver, device=devices[r], rank=r, nranks=nslabs,
                                 ghost=ghost, reach=reach, transport=transport, connect=False) for r in range(nslabs)]
@@ -314,11 +319,13 @@ class LocalSlabGroup:
         self.NumX, self.NumY = self.slabs[0].NumX, self.slabs[0].NumY
 
     def __setattr__(self, name, value):
-        if name in ("UseBFECC", "Confinement", "TurbulenceStrength", "PressureDamping", "SmokeAdvection", "NumIters"):
+        if name in SlabFluid.KNOBS:
             for s in self.slabs:
                 setattr(s, name, value)
-        else:
+        elif name in ("NumX", "NumY") or not name[:1].isupper():
             object.__setattr__(self, name, value)
+        else:
+            raise AttributeError(f"LocalSlabGroup has no knob {name!r}")
 
     def edit(self, cmds):
         for s in self.slabs:

@@ -49,13 +49,18 @@ typedef enum fb_solver {
     /* Lexicographic in-place Gauss-Seidel/SOR, reproduced bit for bit by a
      * skewed-tile wavefront (i + j + 2*sweep ordering).  Single GPU only. */
     FB_SOLVER_EXACT = 0,
-    /* Same per-cell update in red-black order, all iterations fused in one pass.
-     * Order-independent, slab-decomposable; reaches the reference's residual. */
+    /* The same per-cell update (fluid.go:196-229) in red-black order, all iterations fused in one
+     * pass.  Order-independent, slab-decomposable.  NOT the reference's relaxation schedule on the
+     * last iteration: iterations 0 .. n-2 use omega(iter) of fluid.go:169-170 on both colours, the
+     * last one closes with omega = 1.0 (red) and 0.5 (black) whatever fb_params.relaxation is
+     * (omega_schedule_redblack in csrc/fluidb200.cu; DESIGN.md 4.1 says why).  Parity claim of the
+     * red-black modes: max|div| after the solve <= the reference's 8 lexicographic sweeps on the
+     * same input (bench.py prints both); fields differ from the reference's by the size of the
+     * solver residual.  Bit-exact only against this repository's restatement of the same ordering. */
     FB_SOLVER_REDBLACK = 1,
-    /* The same red-black iteration in pressure form: one scalar per cell circulates
-     * through the fused iterations and U, V, p are materialised once.  Algebraically
-     * identical to FB_SOLVER_REDBLACK, rounding differs at the 1e-6 level; ~7x fewer
-     * instructions per cell update.  The throughput solver. */
+    /* The same red-black iteration and schedule in pressure form: one scalar per cell circulates
+     * through the fused iterations and U, V, p are materialised once.  Algebraically identical to
+     * FB_SOLVER_REDBLACK, rounding differs at the 1e-6 level.  The throughput solver. */
     FB_SOLVER_REDBLACK_PRESSURE = 2
 } fb_solver;
 

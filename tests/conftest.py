@@ -9,6 +9,24 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 
+def go_toolchain():
+    """`go version` if a Go toolchain is on PATH, else None.  The reference is pure Go: where Go exists the goldens
+    are re-checked against the reference itself (tests/golden/verify_with_go.sh); here it does not."""
+    import shutil
+    import subprocess
+    exe = shutil.which("go")
+    if not exe:
+        return None
+    try:
+        return subprocess.run([exe, "version"], capture_output=True, text=True, timeout=30).stdout.strip() or None
+    except Exception:
+        return None
+
+
+def pytest_report_header(config):
+    return f"go toolchain: {go_toolchain() or 'absent (goldens pinned by the oracle only: parity unpinned by the reference)'}"
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with `-m gpu`)")
     config.addinivalue_line("markers", "slow: long-running CPU test")

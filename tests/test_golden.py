@@ -40,3 +40,18 @@ def test_cuda_reproduces_golden(name):
     p = make()
     with fluid_b200.New(p.density, p.width, p.height, p.h, solver=solver) as f:
         _run(f, name)
+
+
+def test_goldens_against_the_go_reference():
+    """Where a Go toolchain and the reference checkout exist, the committed goldens must equal the output of the
+    REAL reference (go/cmd/dump driven by tests/golden/verify_with_go.sh), bit for bit.  Skipped -- and parity stays
+    "unpinned" -- where they do not (this image, the GPU boxes)."""
+    import subprocess
+    from conftest import go_toolchain
+    ref = os.environ.get("FLUID_REFERENCE", "/root/reference")
+    if not go_toolchain():
+        pytest.skip("no Go toolchain: goldens pinned by the oracle only")
+    if not os.path.isdir(os.path.join(ref, "pkg", "fluid")):
+        pytest.skip("no reference checkout at " + ref)
+    r = subprocess.run([os.path.join(GOLDEN, "verify_with_go.sh"), ref], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
