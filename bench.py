@@ -142,18 +142,37 @@ def build_preset(name, width, height, bfecc, confinement):
     return presets.jet(width, height, bfecc=bfecc)
 
 
-def cpu_reference_run(workload, steps, warmup, sample_size=None):
-    """The C restatement of the Go reference (oracle/) on the host cores, all threads, on a
-    bounded sample of the workload: the same preset at a grid the CPU finishes in seconds
-    (per-cell work is size-independent: h and dt are not rescaled)."""
+def go_probe():
+    """`go version` when a Go toolchain is on PATH (then the reference itself could be timed), else "absent"."""
+    import shutil
+    exe = shutil.which("go")
+    if not exe:
+        return "absent"
+    try:
+        return subprocess.run([exe, "version"], capture_output=True, text=True, timeout=30).stdout.strip() or "absent"
+    except Exception:
+        return "absent"
+
+
+def cpu_reference_run(workload, steps, warmup, sample_size=None, budget_s=420.0):
+    """The C restatement of the Go reference (oracle/) on the host cores, all threads, on the SAME preset and grid as
+    the GPU arm (`sample_size` shrinks the grid; the caller then says so).  The first warm-up step is timed: if
+    (warmup + steps) of them would not fit `budget_s`, warm-up and steps are cut (never below 1 + 2) and the line
+    reports what was actually run."""
     import oracle
     pname, w, h, bfecc, conf, _ = WORKLOADS[workload]
-    if sample_size is None:
-        sample_size = (min(w, 1024), min(h, 1024))
-    sw, sh = sample_size
+    sw, sh = sample_size if sample_size is not None else (w, h)
     p = build_preset(pname, sw, sh, bfecc, conf)
     f = make_fluid(oracle, p, oracle.SOLVER_EXACT)
-    f.step(p.dt, warmup, p.per_step)
+    t0 = time.perf_counter()
+    f.step(p.dt, 1, p.per_step)
+    first = time.perf_counter() - t0
+    asked = (steps, warmup)
+    if first * (warmup + steps) > budget_s:
+        warmup = 1
+        steps = max(2, min(steps, int(budget_s / max(first, 1e-9)) - 1))
+    if warmup > 1:
+        f.step(p.dt, warmup - 1, p.per_step)
     t0 = time.perf_counter()
     f.step(p.dt, steps, p.per_step)
     dt = time.perf_counter() - t0
@@ -162,7 +181,24 @@ def cpu_reference_run(workload, steps, warmup, sample_size=None):
             "sample": f"{pname} preset {sw}x{sh} (+ring), bfecc={bfecc}, confinement={conf}, {steps} steps after "
                       f"{warmup} warm-up, oracle/ C restatement of the Go reference (lexicographic solver), "
                       f"{int(f.threads)} threads (GOMAXPROCS-equivalent), nproc={os.cpu_count()}",
-            "ms_per_step": dt / steps * 1e3}
+            "ms_per_step": dt / steps * 1e3, "steps_run": steps, "warmup_run": warmup, "asked": asked,
+            "grid": [sw + 2, sh + 2], "same_grid_as_gpu_arm": (sw, sh) == (w, h)}
+
+
+def cpu_anchor_config1():
+    """BASELINE config[0] / the reference's own BenchmarkSimulateWithJet (pkg/fluid/fluid_bench_test.go:29-43): the jet
+    preset at the default 302x253 grid, BFECC off, 600 steps; the author quotes ~4.6 ms/step on an Apple M4 Max."""
+    import oracle
+    p = build_preset("jet", 300, 251, False, 0.0)
+    f = make_fluid(oracle, p, oracle.SOLVER_EXACT)
+    f.step(p.dt, 20, p.per_step)
+    t0 = time.perf_counter()
+    f.step(p.dt, 600, p.per_step)
+    dt = time.perf_counter() - t0
+    return {"ms_per_step": dt / 600 * 1e3, "cell_steps_per_s": f.NumX * f.NumY * 600 / dt, "steps": 600, "grid": [f.NumX, f.NumY],
+            "threads": int(f.threads), "reference_author_ms_per_step": 4.6,
+            "note": "oracle/ C restatement, jet preset as main/ runs it (jet re-imposed every step); the author's figure is "
+                    "Go on an Apple M4 Max (fluid_bench_test.go:29)"}
 
 
 def dist_env():
@@ -339,14 +375,10 @@ def run_projection(args, rank, world, local):
     proj_ms = allmax(phases["project"][0] / max(phases["project"][1], 1))
     cells_rank = (f.i_hi - f.i_lo) * NY
     achieved = 24 * cells_rank / (proj_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            traffic = json.load(fh).get(args.workload, {}).get("project")
-    except Exception:
-        traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_rbq_fused" if args.solver == "pressure" else "k_rb_fused", "phase": "project",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    kname = "k_rbq_stream" if args.solver == "pressure" else "k_rb_fused"
+    traffic, traffic_src = traffic_for(args.workload, kname)
+    roofline = {"bound": "hbm", "kernel": kname, "phase": "project",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "alg_bytes_per_cell": 24.0, "ms_per_launch": proj_ms,
                 "share_of_step": proj_ms / (ms / args.steps),
                 "pressure_solve": {"alg_bytes_per_cell": 24, "ms": proj_ms, "achieved": achieved, "frac": achieved / peak,
@@ -408,52 +440,114 @@ def run_projection(args, rank, world, local):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="karman4096", choices=sorted(WORKLOADS))
-    ap.add_argument("--solver", default="pressure", choices=["pressure", "redblack", "exact"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo exchange between slabs (N > 1)")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the exact-solver and e2e legs")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+def source_stamp():
+    """sha1 of the kernel sources: profiles/*_traffic.json carries the stamp of the build its ncu captures were taken
+    from, and `roofline.traffic` is only reported when it matches THIS build."""
+    import hashlib
+    hh = hashlib.sha1()
+    csrc = os.path.join(ROOT, "fluid_b200", "csrc")
+    for fn in sorted(os.listdir(csrc)):
+        if fn.endswith((".cu", ".cuh")):
+            with open(os.path.join(csrc, fn), "rb") as fh:
+                hh.update(fh.read())
+    return hh.hexdigest()[:16]
 
-    rank, world, local = dist_env()
-    pname, width, height, bfecc, conf, cfg_desc = WORKLOADS[args.workload]
-    if pname == "projection":
-        return run_projection(args, rank, world, local)
-    bpc = step_bytes(bfecc, conf)
 
-    if args.impl == "reference":
-        # rank 0 alone runs the CPU implementation; other ranks exit without work
-        if rank != 0:
-            return 0
-        r = cpu_reference_run(args.workload, args.steps, args.warmup)
-        line = {
-            "impl": "reference", "metric": "cell-steps/s", "value": r["value"], "unit": "cell-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "restates": cfg_desc, "solver": "lexicographic (reference)"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": r["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line))
-        return 0
+def traffic_for(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the newest profiles/rNN_traffic.json whose stamp matches this build."""
+    prof = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(fn for fn in os.listdir(prof) if fn.endswith("_traffic.json"))
+    except OSError:
+        return None, "no profiles/"
+    stamp = source_stamp()
+    for fn in reversed(names):
+        try:
+            with open(os.path.join(prof, fn)) as fh:
+                d = json.load(fh)
+        except Exception:
+            continue
+        if d.get("source_stamp") != stamp:
+            continue
+        v = d.get(workload, {}).get(kernel)
+        if v is not None:
+            return v, fn
+    return None, f"no ncu capture of this build (source stamp {stamp}); see tools/collect_profiles.sh"
 
+
+def residual_on_state(sim, preset, fluid_b200):
+    """The benchmarked solver's parity claim ON THE BENCHMARKED STATE: the projection's input of the next step (the
+    per-frame edits applied to the final state of the timed region) goes through the reference's 8 lexicographic sweeps
+    (oracle, CPU) and through the GPU solver's 8 iterations; max|div| over the cells the projection updates before and
+    after both.  north_star: an order-dependent reference solver is matched by residual, with the iteration count stated."""
+    import oracle
+    sim.edit(preset.per_step)
+    state = {k: sim.get(k) for k in ("U", "V", "M", "p")}
+    o = oracle.New(preset.density, preset.width, preset.height, preset.h, solver=oracle.SOLVER_EXACT)
+    o.edit(preset.init)
+    o.set("U", state["U"]); o.set("V", state["V"])
+    before = float(o.MaxDivergence())
+    t0 = time.perf_counter()
+    o.project(8, preset.dt)
+    lex_s = time.perf_counter() - t0
+    lex = float(o.MaxDivergence())
+    o.close()
+    gpu_before = float(sim.MaxDivergence())
+    sim.project(8, preset.dt)
+    gpu = float(sim.MaxDivergence())
+    for k, v in state.items():        # put the state back: later legs continue from it
+        sim.set(k, v)
+    return {"max_div_before": before, "gpu_before": gpu_before, "gpu_after_8": gpu, "reference_lex_after_8": lex,
+            "iterations": 8, "ok": bool(gpu <= lex), "reference_solve_s": lex_s,
+            "what": "input = final state of the timed region + the per-frame edits; reference = oracle/ lexicographic GS/SOR, "
+                    "8 sweeps (fluid.go:157-234); gpu = the benchmarked solver, 8 iterations; MaxDivergence() of fluid.go:876"}
+
+
+def slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, transport):
+    """N ranks vs one GPU on the same small preset (Karman, BFECC + confinement, pressure-form solver): every field must
+    be bit-identical.  Runs inside the driver's own SCALE invocation so that N-process correctness is on record."""
+    from fluid_b200 import presets
+    width, height, steps = 160 * world, 96, 10
+    p = presets.karman(width, height)
+    solver = fluid_b200.SOLVER_REDBLACK_PRESSURE
+    reach = parallel.reach_for(p.dt, p.h, 8.0)
+    sim = parallel.SlabFluid(p.density, width, height, p.h, solver=solver, device=local, rank=rank, nranks=world,
+                             ghost=parallel.required_ghost(reach, True, True), reach=reach, transport=transport)
+    sim.edit(p.init)
+    sim.UseBFECC = True
+    sim.Confinement = 0.1
+    sim.step(p.dt, steps, p.per_step)
+    sim.check_halo()
+    got = {k: sim.get(k) for k in ("U", "V", "M", "p")}
+    sim.close()
+    out = None
+    if rank == 0:
+        one = fluid_b200.New(p.density, width, height, p.h, solver=solver, device=local)
+        one.edit(p.init)
+        one.UseBFECC = True
+        one.Confinement = 0.1
+        one.step(p.dt, steps, p.per_step)
+        diffs = {k: float(np.max(np.abs(got[k].astype(np.float64) - one.get(k).astype(np.float64)))) for k in got}
+        one.close()
+        out = {"ok": all(v == 0.0 for v in diffs.values()), "max_abs_diff": diffs, "ranks": world, "grid": [width + 2, height + 2],
+               "steps": steps, "what": "Karman preset, BFECC + confinement, pressure-form solver: N row slabs (peer-memory halo "
+                                        "exchange) vs the single-GPU run of the same grid, U V M p compared bit for bit"}
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+def run_preset(args, workload, rank, world, local, primary):
+    """One preset workload on `world` GPUs (weak scaling over i); returns the JSON line's dict on rank 0."""
     import torch
     import torch.distributed as dist
 
     import fluid_b200
     from fluid_b200 import _lib as L
+    from fluid_b200 import parallel
 
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+    pname, width, height, bfecc, conf, cfg_desc = WORKLOADS[workload]
+    bpc = step_bytes(bfecc, conf)
 
     def barrier():
         if world > 1:
@@ -464,9 +558,8 @@ def main():
               "exact": fluid_b200.SOLVER_EXACT}[args.solver]
     preset = build_preset(pname, width, height, bfecc, conf)
 
-    # ---- N > 1: weak scaling -- the grid grows with N along i (row slabs, one per GPU), every
-    # rank steps its slab, halos go over NCCL (fluid_b200.parallel); N == 1 is the plain handle.
-    from fluid_b200 import parallel
+    # ---- N > 1: weak scaling -- the grid grows with N along i (row slabs, one per GPU), every rank steps its slab,
+    # halos travel through peer memory (fluid_b200.parallel); N == 1 is the plain handle.
     if world > 1:
         if solver == fluid_b200.SOLVER_EXACT:
             raise SystemExit("the lexicographic solver does not decompose into slabs; use --solver pressure")
@@ -502,76 +595,120 @@ def main():
             ms = float(t.item())
         return ms
 
+    K = args.steps
     run_steps(args.warmup)
     if hasattr(sim, "set_option"):
         sim.set_option(L.OPT_SOLVE_STATS, 0)      # per-iteration residual tracking off in the timed region
-    sim.profile(True)
-    sim.profile_read()
+    # ---- (1) the quiescent state round 1 reported: the jet has moved W + K of NumX lines, most cells are exact zeros
+    quiescent_ms = timed(K)
+    # ---- (2) develop the flow: the jet front (CFL 3.33 lines per step at u = 4) crosses one GPU's share of the domain
+    preroll = args.preroll
+    if preroll < 0:
+        preroll = min(int(np.ceil((width + 2) * preset.h / (4.0 * preset.dt))), args.preroll_cap)
+    done = 0
+    while done < preroll:
+        n = min(256, preroll - done)
+        run_steps(n)
+        done += n
+        if world > 1:
+            sim.check_halo()
+    # ---- (3) the timed region: blocks of EXACTLY K steps, each between barrier + synchronize, CUDA events on the
+    # library's stream, max over ranks; enough blocks for >= args.min_timed_steps steps so that the clock sampler sees the
+    # run.  The reported step time is the MEDIAN block; every block is listed.
+    nblocks = max(1, -(-args.min_timed_steps // K))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     launches0 = sim.launch_count()
-    ms = timed(args.steps)
-    launches = sim.launch_count() - launches0
+    blocks = [timed(K) for _ in range(nblocks)]
+    launches = (sim.launch_count() - launches0) // nblocks
     clk = clocks.stop() if rank == 0 else {}
+    ms = float(np.median(blocks))
+    value = cells_total * K / (ms * 1e-3)
+    # ---- (4) one more block with the per-phase / per-kernel CUDA events on (not part of the headline)
+    sim.profile(True)
+    sim.profile_read()
+    prof_ms = timed(K)
     phases = sim.profile_read()
     sim.profile(False)
-    value = cells_total * args.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant phase and of the whole step
+    # ---- roofline of the dominant kernel (largest share of the step among single kernels) and of the whole step
     peak, peak_src = measured_peak()
     cells_rank = cells_total // world
+    kernel_alg_bytes = {"k_pressure_solve": 24, "k_advect_velocity_full": 20, "k_bfecc_velocity_correct": 28,
+                        "k_advect_smoke_full": 20, "k_bfecc_smoke_correct": 24, "k_confine_turbulence": 20}
+    kernel_real = {"k_pressure_solve": {"pressure": "k_rbq_stream", "redblack": "k_rb_fused", "exact": "k_gs_wavefront"}[args.solver]}
+    kern = {}
+    for k in L.PROF_KERNELS:
+        tot, calls = phases.get(k, (0.0, 0))
+        if calls > 0 and tot > 0:
+            per = tot / calls
+            ach = kernel_alg_bytes[k] * cells_rank / (per * 1e-3) / 1e9
+            kern[kernel_real.get(k, k)] = {"ms_per_launch": per, "launches_per_step": calls / K, "ms_per_step": tot / K,
+                                           "alg_bytes_per_cell": kernel_alg_bytes[k], "achieved": ach, "frac": ach / peak,
+                                           "share_of_step": tot / max(prof_ms, 1e-9)}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    proj = kern.get(kernel_real["k_pressure_solve"], {})
     phase_alg_bytes = {"project": 24, "confinement": 20, "turbulence": 0 if conf != 0.0 else 20,
-                       "advect_velocity": 68 if bfecc else 20, "advect_smoke": 64 if bfecc else 20,
-                       "clear_pressure": 0, "edits": 0, "borders": 0, "viscosity": 0}
-    shares = {k: v[0] for k, v in phases.items() if v[1] > 0}
-    total_phase_ms = sum(shares.values()) or 1.0
-    # dominant KERNEL: a BFECC advection phase is three launches (advect, back-trace+correct, advect);
-    # every other timed phase is one large kernel (plus perimeter-sized helpers)
-    launches_in_phase = {"advect_velocity": 3 if bfecc else 1, "advect_smoke": 3 if bfecc else 1}
-    kernel_names = {"project": {"pressure": "k_rbq_fused", "redblack": "k_rb_fused", "exact": "k_gs_wavefront"}[args.solver],
-                    "confinement": "k_confine_turbulence", "turbulence": "k_confine_turbulence",
-                    "advect_velocity": "k_advect_velocity_full / k_bfecc_velocity_correct (mean of 3 launches)" if bfecc
-                    else "k_advect_velocity_full",
-                    "advect_smoke": "k_advect_smoke_full / k_bfecc_smoke_correct (mean of 3 launches)" if bfecc
-                    else "k_advect_smoke_full"}
-    per_launch = {k: (phases[k][0] / max(phases[k][1], 1)) / launches_in_phase.get(k, 1) for k in shares
-                  if k in kernel_names}
-    dom = max(per_launch, key=per_launch.get) if per_launch else "project"
-    dom_ms = per_launch.get(dom, 0.0)
-    dom_bytes = phase_alg_bytes.get(dom, 0) * cells_rank / launches_in_phase.get(dom, 1)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    proj_ms = phases["project"][0] / max(phases["project"][1], 1)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            traffic = json.load(fh).get(args.workload, {}).get(dom)
-    except Exception:
-        traffic = None
-    roofline = {
-        "bound": "hbm", "kernel": kernel_names.get(dom, dom), "phase": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "alg_bytes_per_cell": phase_alg_bytes.get(dom, 0) / launches_in_phase.get(dom, 1), "ms_per_launch": dom_ms,
-        "share_of_step": shares.get(dom, 0.0) / total_phase_ms,
-        "step": {"alg_bytes_per_cell_step": bpc, "achieved": bpc * cells_rank / (ms / args.steps * 1e-3) / 1e9,
-                 "frac": bpc * cells_rank / (ms / args.steps * 1e-3) / 1e9 / peak},
-        "pressure_solve": {"alg_bytes_per_cell": 24, "ms": proj_ms,
-                           "achieved": 24 * cells_rank / (proj_ms * 1e-3) / 1e9 if proj_ms > 0 else 0.0,
-                           "frac": (24 * cells_rank / (proj_ms * 1e-3) / 1e9 / peak) if proj_ms > 0 else 0.0},
-        "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1] > 0},
-        "phases_frac_of_peak": {k: (phase_alg_bytes.get(k, 0) * cells_rank / (v[0] / max(v[1], 1) * 1e-3) / 1e9 / peak)
+                       "advect_velocity": 68 if bfecc else 20, "advect_smoke": 64 if bfecc else 20}
+    step_gbs = bpc * cells_rank / (ms / K * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src}
+    if dom:
+        d = kern[dom]
+        traffic, traffic_src = traffic_for(workload, dom)
+        roofline.update({"kernel": dom, "achieved": d["achieved"], "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                         "alg_bytes_per_cell": d["alg_bytes_per_cell"], "alg_bytes_per_launch": d["alg_bytes_per_cell"] * cells_rank,
+                         "ms_per_launch": d["ms_per_launch"], "launches_per_step": d["launches_per_step"],
+                         "share_of_step": d["share_of_step"],
+                         "dominant_by": "largest total time per step among single kernels (CUDA events around every launch)"})
+    roofline.update({
+        "step": {"alg_bytes_per_cell_step": bpc, "achieved": step_gbs, "frac": step_gbs / peak},
+        "pressure_solve": {"kernel": kernel_real["k_pressure_solve"], "alg_bytes_per_cell": 24, "ms": proj.get("ms_per_launch"),
+                           "achieved": proj.get("achieved"), "frac": proj.get("frac")},
+        "kernels": kern,
+        "phases_ms_per_step": {k: v[0] / K for k, v in phases.items() if v[1] > 0 and k not in L.PROF_KERNELS},
+        "phases_frac_of_peak": {k: (phase_alg_bytes[k] * cells_rank / (v[0] / K * 1e-3) / 1e9 / peak)
                                 for k, v in phases.items() if v[1] > 0 and v[0] > 0 and phase_alg_bytes.get(k, 0)},
+        "profiled_block_ms_per_step": prof_ms / K})
+
+    line = {
+        "metric": "cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "restates": cfg_desc, "grid_per_gpu": [width + 2, height + 2],
+                   "grid_total": [width * world + 2, height + 2], "cells_total": cells_total, "preset": pname, "bfecc": bfecc,
+                   "confinement": conf, "turbulence": 0.02, "dt": preset.dt, "parallelism": parallelism,
+                   "solver": {"pressure": "red-black SOR in pressure form, 8 iterations fused in one pass (k_rbq_stream), "
+                                          "reference omega schedule with damped close (1.0, 0.5)",
+                              "redblack": "red-black SOR on the face velocities, 8 iterations fused, "
+                                          "reference omega schedule with damped close (1.0, 0.5)",
+                              "exact": "lexicographic GS/SOR (bit-exact wavefront), 8 sweeps"}[args.solver],
+                   "l2": "working set >> 126 MB L2 (inputs larger than L2)" if cells_total // world > 8e6
+                         else "working set fits L2: HBM fraction not meaningful",
+                   "state": f"developed flow: {preroll} untimed pre-roll steps after the {args.warmup} warm-up steps (the jet front "
+                            f"crosses one GPU's {width + 2} lines at 3.33 lines per step); the quiescent start-up state round 1 "
+                            "timed is reported beside it (`quiescent`)",
+                   "timing": f"{nblocks} blocks of exactly {K} steps, CUDA events on the library's stream between barrier + "
+                             "synchronize, max over ranks; value = median block; profiling events off"},
+        "timed_blocks_ms": blocks, "quiescent": {"ms_per_step": quiescent_ms / K, "value": cells_total * K / (quiescent_ms * 1e-3),
+                                                "what": f"the same {K} steps timed right after the warm-up, before the pre-roll"},
+        "roofline": roofline, "gpu_launches": int(launches), "clocks": clk,
     }
+    if not primary:
+        if world > 1:
+            sim.check_halo()
+        sim.close()
+        return line if rank == 0 else None
 
     # ---- e2e: the frame loop through the public API with host buffers
     e2e = None
     secondary = {}
     if (not args.no_secondary) and world == 1:
+        import ctypes as C
         per = fluid_b200.edits.pack(preset.per_step)
         h2d = int(per.nbytes)
         mirror = sim._mirror(L.M)            # pinned host memory owned by the library
-        mn, mx = __import__("ctypes").c_float(), __import__("ctypes").c_float()
-        import ctypes as C
+        mn, mx = C.c_float(), C.c_float()
 
         def frame():
             sim.step(preset.dt, 1, per)      # edit commands host->device + Simulate
@@ -581,7 +718,7 @@ def main():
             frame()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(K):
             frame()
         barrier()
         sync_s = time.perf_counter() - t0
@@ -603,14 +740,14 @@ def main():
         pipelined(3)
         barrier()
         t0 = time.perf_counter()
-        pipelined(args.steps)
+        pipelined(K)
         barrier()
         e2e_s = time.perf_counter() - t0
-        e2e = {"value": cells_total * args.steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(sim.NumX * sim.NumY * 4 + 8), "ms_per_step": e2e_s / args.steps * 1e3,
+        e2e = {"value": cells_total * K / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(sim.NumX * sim.NumY * 4 + 8), "ms_per_step": e2e_s / K * 1e3,
                "what": "per step: edit commands H2D, Simulate, Smoke() view (field + min/max) D2H into pinned memory; "
                        "pipelined frame loop (fb_view_begin/end): the view of step k travels while step k+1 computes",
-               "blocking_loop": {"value": cells_total * args.steps / sync_s, "ms_per_step": sync_s / args.steps * 1e3,
+               "blocking_loop": {"value": cells_total * K / sync_s, "ms_per_step": sync_s / K * 1e3,
                                  "what": "same loop with the blocking fb_view after every step"}}
 
         # ---- the frame loop's neighbours of the hot path, reported beside e2e:
@@ -630,7 +767,7 @@ def main():
         render_loop(3)
         barrier()
         t0 = time.perf_counter()
-        render_loop(args.steps)
+        render_loop(K)
         barrier()
         render_s = time.perf_counter() - t0
         nparts = 1 << 20
@@ -644,7 +781,7 @@ def main():
         alive = sim.AdvectParticles(parts, preset.dt)
         parts_s = time.perf_counter() - t0
         e2e["frame_loop_neighbours"] = {
-            "render_loop": {"value": cells_total * args.steps / render_s, "ms_per_step": render_s / args.steps * 1e3,
+            "render_loop": {"value": cells_total * K / render_s, "ms_per_step": render_s / K * 1e3,
                             "d2h_bytes_per_step": int(sim.NumX * sim.NumY * 4 + 8),
                             "what": "the pipelined frame loop with fb_render_begin/end: the RGBA image of Draw "
                                     "(colormap + solid overlay computed on the device) lands in pinned memory every step"},
@@ -657,8 +794,8 @@ def main():
         other = fluid_b200.SOLVER_EXACT if solver != fluid_b200.SOLVER_EXACT else fluid_b200.SOLVER_REDBLACK_PRESSURE
         sim.Solver = other
         run_steps(2)
-        ms2 = timed(max(args.steps // 3, 3))
-        n2 = max(args.steps // 3, 3)
+        n2 = max(K // 3, 3)
+        ms2 = timed(n2)
         secondary = {"solver": "exact" if other == fluid_b200.SOLVER_EXACT else "pressure",
                      "value": cells_total * n2 / (ms2 * 1e-3), "ms_per_step": ms2 / n2,
                      "note": "exact = lexicographic wavefront, bit-identical to the reference restatement"}
@@ -667,14 +804,9 @@ def main():
     if (not args.no_secondary) and world > 1:
         # frame loop per rank: edit commands H2D, slab step (with its halo exchange), the rank's
         # share of the Smoke() view D2H into pinned memory, min/max all-reduced
-        import ctypes as C
         per = fluid_b200.edits.pack(preset.per_step)
-        # pinned buffer for this rank's slab only; fb_view addresses it as a window of the global array
+        # pinned buffers for this rank's slab only; fb_view addresses them as a window of the global array
         slab = torch.empty(((sim.i_hi - sim.i_lo) * sim.NumY,), dtype=torch.float32, pin_memory=True)
-        view_base = slab.data_ptr() - sim.i_lo * sim.NumY * 4
-        mn, mx = C.c_float(), C.c_float()
-
-        # pipelined frame loop (see the single-GPU leg): two pinned slab buffers per rank
         slabs = [slab, torch.empty_like(slab).pin_memory()]
         bases = [b.data_ptr() - sim.i_lo * sim.NumY * 4 for b in slabs]
 
@@ -694,46 +826,102 @@ def main():
         pipelined(3)
         barrier()
         t0 = time.perf_counter()
-        pipelined(args.steps)
+        pipelined(K)
         barrier()
         t = torch.tensor([time.perf_counter() - t0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-        e2e = {"value": cells_total * args.steps / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(per.nbytes) * world,
-               "d2h_bytes_per_step": int(cells_total * 4 + 8 * world), "ms_per_step": e2e_s / args.steps * 1e3,
+        e2e = {"value": cells_total * K / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(per.nbytes) * world,
+               "d2h_bytes_per_step": int(cells_total * 4 + 8 * world), "ms_per_step": e2e_s / K * 1e3,
                "what": "per step and rank: edit commands H2D, slab Simulate + halo exchange, slab of the Smoke() view D2H "
                        "into pinned memory, min/max all-reduce; pipelined frame loop (fb_view_begin/end)"}
 
-    # residual actually reached by the headline solver on the final state
-    st = sim.solve_stats() if hasattr(sim, "solve_stats") else {}
-    max_div_after = sim.MaxDivergence()
+    # ---- the benchmarked solver against the reference's on the benchmarked state, the CPU baseline at the SAME grid
+    residual, cpu = None, None
     if world > 1:
         sim.check_halo()
-
-    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.workload, 8, 2)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        residual = residual_on_state(sim, preset, fluid_b200)
+        r = cpu_reference_run(workload, 2, 1, budget_s=60.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "grid", "same_grid_as_gpu_arm")}
+        cpu["go_toolchain"] = go_probe()
+        cpu["config1_anchor"] = cpu_anchor_config1()
+    sim.close()
+    line.update({"cpu_baseline": cpu, "e2e": e2e, "other_solver": secondary})
+    line["config"]["residual"] = residual
+    return line if rank == 0 else None
 
-    if rank == 0:
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="karman4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--solver", default="pressure", choices=["pressure", "redblack", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo exchange between slabs (N > 1)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the e2e, other-solver, parity-check and config[3] legs")
+    ap.add_argument("--preroll", type=int, default=-1, help="untimed steps that develop the flow (-1: the jet front crosses one GPU's lines)")
+    ap.add_argument("--preroll-cap", type=int, default=1500)
+    ap.add_argument("--min-timed-steps", type=int, default=200, help="timed blocks of --steps steps are repeated up to this many steps")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local = dist_env()
+    pname, width, height, bfecc, conf, cfg_desc = WORKLOADS[args.workload]
+    if pname == "projection":
+        return run_projection(args, rank, world, local)
+
+    if args.impl == "reference":
+        # rank 0 alone runs the CPU implementation of the SAME preset at the SAME grid; other ranks exit without work.
+        # Nothing of the product is loaded here: presets / edit lists are pure Python, the library opens on first use.
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(args.workload, args.steps, args.warmup)
         line = {
-            "metric": "cell-steps/s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "restates": cfg_desc, "grid_per_gpu": [width + 2, height + 2], "grid_total": [width * world + 2, height + 2],
-                       "cells_total": cells_total, "preset": pname, "bfecc": bfecc, "confinement": conf,
-                       "turbulence": 0.02, "dt": preset.dt, "parallelism": parallelism,
-                       "solver": {"pressure": "red-black SOR in pressure form, 8 iterations fused in one pass, "
-                                              "reference omega schedule with damped close (1.0, 0.5)",
-                                  "redblack": "red-black SOR on the face velocities, 8 iterations fused, "
-                                              "reference omega schedule with damped close (1.0, 0.5)",
-                                  "exact": "lexicographic GS/SOR (bit-exact wavefront), 8 sweeps"}[args.solver],
-                       "l2": "working set >> 126 MB L2 (inputs larger than L2)" if cells_total // world > 8e6
-                             else "working set fits L2: HBM fraction not meaningful",
-                       "residual": {"max_div_after_last_step": max_div_after, "sweeps": st.get("sweeps_run")}},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clk, "other_solver": secondary,
+            "impl": "reference", "metric": "cell-steps/s", "value": r["value"], "unit": "cell-steps/s",
+            "n_gpus": args.gpus, "steps": r["steps_run"], "warmup": r["warmup_run"], "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "restates": cfg_desc, "grid_per_gpu": r["grid"], "preset": pname, "bfecc": bfecc,
+                       "confinement": conf, "solver": "lexicographic GS/SOR, 8 sweeps (the reference's)",
+                       "asked_steps_warmup": list(r["asked"]), "go_toolchain": go_probe(),
+                       "what": "oracle/ (C restatement of the Go reference, parallelRange chunking on all host threads) on the same "
+                               "preset and grid as the GPU arm; one rank's grid whatever --gpus is"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
         }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    line = run_preset(args, args.workload, rank, world, local, primary=True)
+    if not args.no_secondary:
+        if world > 1:
+            import fluid_b200
+            from fluid_b200 import parallel
+            pc = slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, args.transport)
+            if rank == 0:
+                line["parity_check"] = pc
+        if args.workload == "karman4096":
+            # BASELINE configs[3] (jet 16384^2 per GPU, weak scaling) inside the driver's default invocation
+            import copy
+            a2 = copy.copy(args)
+            a2.min_timed_steps = args.steps
+            a2.preroll, a2.preroll_cap = -1, 600
+            extra = run_preset(a2, "jet16384", rank, world, local, primary=False)
+            if rank == 0:
+                line["config3_jet16384"] = {k: extra[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "config", "quiescent",
+                                                                   "timed_blocks_ms", "roofline")}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

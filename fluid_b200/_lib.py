@@ -32,7 +32,11 @@ FLAG_LITERAL, FLAG_EXACT_SHADOW = 1, 2
 VIEW_SMOKE, VIEW_PRESSURE, VIEW_VELOCITY_MAGNITUDE, VIEW_VORTICITY = range(4)
 REDUCE_MAX_DIVERGENCE, REDUCE_MAX_ABS_VELOCITY = range(2)
 PROF_PHASES = ("edits", "clear_pressure", "viscosity", "project", "confinement", "turbulence", "borders",
-               "advect_velocity", "advect_smoke")
+               "advect_velocity", "advect_smoke",
+               # single kernels, one event pair per launch (inside the phase pairs above)
+               "k_pressure_solve", "k_advect_velocity_full", "k_bfecc_velocity_correct", "k_advect_smoke_full",
+               "k_bfecc_smoke_correct", "k_confine_turbulence")
+PROF_KERNELS = PROF_PHASES[9:]
 
 
 class Config(C.Structure):

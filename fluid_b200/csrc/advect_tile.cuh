@@ -1,0 +1,346 @@
+// advect_tile.cuh -- semi-Lagrangian velocity advection (fluid.go:291-398) and the BFECC back-trace + correct pass
+// (fluid.go:938-987, 1094-1120) on shared-memory tiles.
+//
+// k_advect_velocity_full / k_bfecc_velocity_correct (advect_fused.cuh) gather their bilinear taps straight from global
+// memory with 64-bit address arithmetic, and a thread owns 4 consecutive cells, so every tap is a 16-byte-strided warp
+// access: 4 L1 wavefronts per tap instruction (ncu round 1: LSU data pipe 83 %, issue slots 81 %, ~180 / ~260
+// instructions per cell, 0.50 / 0.47 of the HBM peak).  Here a CTA owns the tile of AT_TI lines x AT_TJ columns with the
+// GLOBAL index (ty, tx) -- tile origins are multiples of (AT_TI, AT_TJ) whatever line range a launch covers:
+//   * the sampled planes plus a halo of AT_R + 1 lines / 8 columns are staged in shared memory by TMA (one
+//     cp.async.bulk per line and field, completion counted on one mbarrier);
+//   * ONE LANE PER CELL along j: the four taps of a warp are unit-stride LDS (one wavefront each), at 32-bit shared
+//     addresses with immediate offsets (+1, +pitch, +pitch+1);
+//   * a tap pair that lies inside the staged region needs neither the `min(x0+1, NumX-1)` collapse nor the
+//     `min(floor, NumX-1)` clamp of fluid.go:373-377 (the region ends at NumX-1 / NumY-1 at the latest), and in a tile
+//     whose staged region lies inside [2, NumX-3] x [2, NumY-3] the coordinate clamps of fluid.go:363-364 are provably
+//     no-ops too (an in-region tap pair means h <= x <= NumX*h), so they are skipped;
+//   * a per-tile flag built with the neighbour mask (k_tile_flags: every cell of the tile is an interior fluid cell
+//     with fluid on its -x and -y side) selects a straight-line body without the active / ring / stale-scratch cases
+//     of fluid.go:300-317 -- all of a preset's domain except walls and obstacles;
+//   * a trace that leaves the staged region (|dt*u| > AT_R cells, or the domain edge) falls back to the global
+//     sampler sample_fast<> on the ORIGINAL coordinates, out of line: same result, slower, rare.
+// The arithmetic per face is the reference's, operation for operation (same code as sample_fast).
+#pragma once
+#include "advect_fused.cuh"
+#include "rbq_fused.cuh"      // mbarrier / TMA helpers
+
+#ifndef AT_TI
+#define AT_TI 32              // lines per tile
+#endif
+#define AT_TJ 128             // columns per tile
+#ifndef AT_R
+#define AT_R 6                // a back-trace may land up to AT_R lines / columns away (dt*|u|/h < AT_R - 1)
+#endif
+#define AT_CH 8               // staged columns left of the tile (>= AT_R + 1, multiple of 4: 16-byte TMA granules)
+#define AT_PW (AT_TJ + 2 * AT_CH)        // staged columns: 144
+#define AT_TL (AT_TI + 2 * (AT_R + 1))   // staged lines of a sampled plane
+#define AT_THREADS 256
+#define AT_SMEM (2 * AT_TL * AT_PW * 4 + 16)
+// BFECC correct: U, V with a one-line halo (trace velocities, 3x3 clamp) + fwdU, fwdV with the full halo
+#ifndef AT_BTI
+#define AT_BTI 16
+#endif
+#define AT_BTL (AT_BTI + 2 * (AT_R + 1))
+#define AT_BVL (AT_BTI + 2)
+#define AT_BSMEM ((2 * AT_BTL + 2 * AT_BVL) * AT_PW * 4 + 16)
+static_assert(AT_CH >= AT_R + 1 && AT_CH % 4 == 0, "column halo");
+static_assert(AT_TI % AT_BTI == 0, "a BFECC tile lies inside one flag tile");
+
+struct ATile {
+    int ls0, cs0;             // global line / column of staged element (0, 0) of the SAMPLED planes
+    int vl0, vc0;             // first line / column a tap pair may START on
+    unsigned nl, nc;          // ... and how many: x0 in [vl0, vl0 + nl), x0 + 1 still staged (and <= NumX-1); y alike
+};
+
+// ---- per-tile flags, rebuilt with the mask (only when S changes) ---------------------------------
+// 1: every cell of tile (ty, tx) lies in 1..NumX-2 x 1..NumY-2, is resident on this rank and has MK_C, MK_XM, MK_YM
+__global__ void __launch_bounds__(AT_THREADS) k_tile_flags(const Grid g, const unsigned char *__restrict__ mask, unsigned char *__restrict__ flags,
+                                                           const int ntx)
+{
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int i0 = ty * AT_TI, j = tx * AT_TJ + (threadIdx.x & 127);
+    int ok = 1;
+    for (int i = i0 + (threadIdx.x >> 7); i < i0 + AT_TI; i += AT_THREADS / 128) {
+        const bool inside = i >= 1 && i <= g.NX - 2 && j >= 1 && j <= g.NY - 2 && i >= g.i_alloc0 && i < g.i_alloc0 + g.lines_alloc;
+        if (!inside || (mask[g.at(i, j)] & (MK_C | MK_XM | MK_YM)) != (MK_C | MK_XM | MK_YM)) ok = 0;
+    }
+    ok = __syncthreads_and(ok);
+    if (threadIdx.x == 0) flags[ty * ntx + tx] = (unsigned char)ok;
+}
+
+// the rare path, kept out of line so that the tile loop stays compact
+template <int FLD, bool CHECK>
+__device__ __noinline__ float sample_far(const AdvCtx &c, const float *__restrict__ gdata, const float x, const float y, int *bad)
+{
+    return sample_fast<FLD, CHECK>(c, gdata, x, y, bad);
+}
+
+// sampleField (fluid.go:357-398) with the taps in the staged tile `sm`; `gdata` is the same plane in global memory.
+template <int FLD, bool INTERIOR, bool CHECK>
+__device__ __forceinline__ float sample_tile(const AdvCtx &c, const ATile &T, const float *__restrict__ sm, const float *__restrict__ gdata,
+                                             const float x, const float y, int *bad)
+{
+    float xc = x, yc = y;
+    if (!INTERIOR) {
+        xc = fmaxf(fminf(x, c.xmax), c.h);
+        yc = fmaxf(fminf(y, c.ymax), c.h);
+    }
+    const float xs = (FLD == 0) ? xc : xc - c.h2;
+    const float ys = (FLD == 1) ? yc : yc - c.h2;
+    const float2 s2 = make_float2(xs, ys), h1 = make_float2(c.h1, c.h1);
+    const float2 q = __fmul2_rn(s2, h1);
+    const float fx = floorf(q.x), fy = floorf(q.y);
+    const int x0 = (int)fx, y0 = (int)fy;
+    if ((unsigned)(x0 - T.vl0) < T.nl && (unsigned)(y0 - T.vc0) < T.nc) {
+        const float2 f0h = __fmul2_rn(make_float2(fx, fy), make_float2(c.h, c.h));
+        const float2 t = __fmul2_rn(__fadd2_rn(s2, make_float2(-f0h.x, -f0h.y)), h1);
+        const float2 sxy = __fadd2_rn(make_float2(1.0f, 1.0f), make_float2(-t.x, -t.y));
+        const float *p = sm + (x0 - T.ls0) * AT_PW + (y0 - T.cs0);
+        const float f00 = p[0], f10 = p[AT_PW], f11 = p[AT_PW + 1], f01 = p[1];
+        // the four weights as scalar products (the pairs (sx, tx) a packed product needs would have to be assembled
+        // with moves), the four weighted taps as two packed products
+        const float w00 = sxy.x * sxy.y, w10 = t.x * sxy.y, w11 = t.x * t.y, w01 = sxy.x * t.y;
+        const float2 pA = __fmul2_rn(make_float2(w00, w10), make_float2(f00, f10));
+        const float2 pB = __fmul2_rn(make_float2(w01, w11), make_float2(f01, f11));
+        return ((pA.x + pA.y) + pB.y) + pB.x;
+    }
+    return sample_far<FLD, CHECK>(c, gdata, x, y, bad);
+}
+
+// Stage lines [ls0, ls0 + nlines) x columns [cs0, cs0 + AT_PW) of `src` (clipped to the lines this rank holds and to the
+// pitch) into `dst`; called by warp 0, one line per lane and round.  `issue` false: only count the bytes this lane will ask for.
+__device__ __forceinline__ unsigned at_stage_field(const AdvCtx &c, float *dst, const float *__restrict__ src, const int ls0, const int nlines,
+                                                   const int cs0, const int lane, const unsigned bar, const bool issue)
+{
+    const int la = max(ls0, max(c.i_alloc0, 0)), lb = min(ls0 + nlines, min(c.i_alloc0 + c.lines_alloc, c.NX));
+    const int ca = max(cs0, 0), cb = min(cs0 + AT_PW, c.pitch);
+    if (cb <= ca) return 0;
+    const unsigned bytes = (unsigned)(cb - ca) * 4u;
+    unsigned total = 0;
+#pragma unroll 1
+    for (int l = la + lane; l < lb; l += 32) {
+        if (issue) rq_tma_load(rq_s32(dst + (l - ls0) * AT_PW + (ca - cs0)), src + (size_t)(l - c.i_alloc0) * c.pitch + ca, bytes, bar);
+        total += bytes;
+    }
+    return total;
+}
+
+__device__ __forceinline__ void at_tile_geometry(const AdvCtx &c, ATile &T, const int nlines)
+{
+    // lines / columns that are staged AND exist: a tap pair may start on [v0, v1 - 1]
+    const int la = max(T.ls0, max(c.i_alloc0, 0)), lb = min(T.ls0 + nlines, min(c.i_alloc0 + c.lines_alloc, c.NX));
+    const int ca = max(T.cs0, 0), cb = min(T.cs0 + AT_PW, c.NY);
+    T.vl0 = la; T.nl = (unsigned)max(lb - 1 - la, 0);
+    T.vc0 = ca; T.nc = (unsigned)max(cb - 1 - ca, 0);
+}
+
+__device__ __forceinline__ void at_wait_tiles(unsigned long long *bar, int *bad)
+{
+    // every thread waits for the tiles (bounded: a copy that never lands latches the error flag instead of hanging)
+    const unsigned b = rq_s32(bar);
+    bool ok = false;
+#pragma unroll 1
+    for (int k = 0; k < (1 << 17) && !ok; k++) ok = rq_mbar_try_a(b, 0);
+    if (!ok && bad) *bad = 3;
+}
+
+// FAST: the tile is interior (no coordinate clamps) and all its cells are active (flag of k_tile_flags): every face is
+// traced, no ring, no stale-scratch fall-back.
+template <bool FAST, bool CHECK>
+__device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &T, const float *__restrict__ sU, const float *__restrict__ sV,
+                                                  const float *__restrict__ trU, const float *__restrict__ trV,
+                                                  const unsigned char *__restrict__ mask, const float *__restrict__ shU,
+                                                  const float *__restrict__ shV, float *__restrict__ dstU, float *__restrict__ dstV,
+                                                  const float dt, const int i0, const int i1, const int j, int *bad)
+{
+    if (j >= c.NY) return;
+    const float yj = (float)j * c.h;
+    const float yj2 = yj + c.h2;
+    const int ifirst = i0 + (int)(threadIdx.x >> 7);
+    const float *pu = sU + (ifirst - T.ls0) * AT_PW + (j - T.cs0), *pv = sV + (ifirst - T.ls0) * AT_PW + (j - T.cs0);
+    size_t o = (size_t)(ifirst - c.i_alloc0) * c.pitch + j;
+    const size_t ostep = (size_t)(AT_THREADS / 128) * c.pitch;
+#pragma unroll 2
+    for (int i = ifirst; i < i1; i += AT_THREADS / 128, pu += (AT_THREADS / 128) * AT_PW, pv += (AT_THREADS / 128) * AT_PW, o += ostep) {
+        const float u = pu[0], v = pv[0];
+        const float xi = (float)i * c.h;
+        float outU, outV;
+        if (FAST) {
+            const float av = (((pv[-AT_PW] + v) + pv[-AT_PW + 1]) + pv[1]) * 0.25f;        // avgV (fluid.go:342-347)
+            const float au = (((pu[-1] + u) + pu[AT_PW - 1]) + pu[AT_PW]) * 0.25f;         // avgU (fluid.go:335-340)
+            const float du = dt * u, dv = dt * av;
+            outU = sample_tile<0, true, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
+            const float du2 = dt * au, dv2 = dt * v;
+            outV = sample_tile<1, true, CHECK>(c, T, sV, trV, (xi + c.h2) - du2, yj - dv2, bad);
+        } else {
+            const unsigned m = mask[o];
+            const bool in_loop = i >= 1 && j >= 1;                       // loops start at 1 (fluid.go:300-301); j < NumY holds
+            const bool act_u = in_loop && (m & MK_C) && (m & MK_XM) && j < c.NY - 1;
+            const bool act_v = in_loop && (m & MK_C) && (m & MK_YM) && i < c.NX - 1;
+            const bool ring = i == 0 || j == 0 || i == c.NX - 1 || j == c.NY - 1;
+            if (act_u) {
+                // avgV (fluid.go:342-347): V[i-1,j] + V[i,j] + V[i-1,j+1] + V[i,j+1]
+                const float av = (((pv[-AT_PW] + v) + pv[-AT_PW + 1]) + pv[1]) * 0.25f;
+                const float du = dt * u, dv = dt * av;
+                outU = sample_tile<0, false, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
+            } else {
+                outU = ring ? u : shU[o];
+            }
+            if (act_v) {
+                // avgU (fluid.go:335-340): U[i,j-1] + U[i,j] + U[i+1,j-1] + U[i+1,j]
+                const float au = (((pu[-1] + u) + pu[AT_PW - 1]) + pu[AT_PW]) * 0.25f;
+                const float du = dt * au, dv = dt * v;
+                outV = sample_tile<1, false, CHECK>(c, T, sV, trV, (xi + c.h2) - du, yj - dv, bad);
+            } else {
+                outV = ring ? v : shV[o];
+            }
+        }
+        dstU[o] = outU;
+        dstV[o] = outV;
+    }
+}
+
+// advectVelocity writing complete planes: same contract as k_advect_velocity_full (tr*: the planes that are traced
+// through AND sampled; sh*: the stale scratch values skipped faces fall back to, Q-6).  blockIdx.y counts tiles from
+// the one that holds line ib.
+template <bool CHECK>
+__global__ void __launch_bounds__(AT_THREADS)
+k_advect_velocity_tile(const AdvCtx c, const float *__restrict__ trU, const float *__restrict__ trV,
+                       const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
+                       const float *__restrict__ shU, const float *__restrict__ shV, float *__restrict__ dstU,
+                       float *__restrict__ dstV, const float dt, const int ib, const int ie, int *bad)
+{
+    extern __shared__ __align__(128) unsigned char at_smem[];
+    float *sU = reinterpret_cast<float *>(at_smem), *sV = sU + AT_TL * AT_PW;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sV + AT_TL * AT_PW);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ty = ib / AT_TI + blockIdx.y;
+    const int i0 = max(ty * AT_TI, ib), i1 = min((ty + 1) * AT_TI, ie);
+    const int j0 = blockIdx.x * AT_TJ;
+    ATile T;
+    T.ls0 = ty * AT_TI - (AT_R + 1); T.cs0 = j0 - AT_CH;
+    at_tile_geometry(c, T, AT_TL);
+    if (tid == 0) rq_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned b = rq_s32(bar);
+        unsigned bytes = at_stage_field(c, sU, trU, T.ls0, AT_TL, T.cs0, lane, b, false) + at_stage_field(c, sV, trV, T.ls0, AT_TL, T.cs0, lane, b, false);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        if (lane == 0) rq_mbar_expect_tx(bar, bytes);      // the one arrival of the phase, with the bytes of all lanes
+        __syncwarp();
+        at_stage_field(c, sU, trU, T.ls0, AT_TL, T.cs0, lane, b, true);
+        at_stage_field(c, sV, trV, T.ls0, AT_TL, T.cs0, lane, b, true);
+    }
+    // interior tile: everything staged lies in [2, NumX-3] x [2, NumY-3] (and is resident) -> the coordinate clamps
+    // cannot trigger for in-region taps; all cells active: flag of k_tile_flags
+    const bool fast = T.ls0 >= 2 && T.ls0 + AT_TL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
+                      T.ls0 >= c.i_alloc0 && T.ls0 + AT_TL <= c.i_alloc0 + c.lines_alloc && tile_flags[ty * ntx + blockIdx.x] != 0;
+    at_wait_tiles(bar, bad);
+    const int j = j0 + (tid & 127);
+    if (fast) at_velocity_cells<true, CHECK>(c, T, sU, sV, trU, trV, mask, shU, shV, dstU, dstV, dt, i0, i1, j, bad);
+    else at_velocity_cells<false, CHECK>(c, T, sU, sV, trU, trV, mask, shU, shV, dstU, dstV, dt, i0, i1, j, bad);
+}
+
+// ---- BFECC velocity: back-trace (+dt, sampling the forward result), error compensation and clamp to the 3x3
+// neighbourhood of the original field in one pass (fluid.go:938-987, 1094-1120); contract of k_bfecc_velocity_correct.
+template <bool FAST, bool CHECK>
+__device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, const float *__restrict__ sU, const float *__restrict__ sV,
+                                               const float *__restrict__ sFU, const float *__restrict__ sFV, const int vls0,
+                                               const float *__restrict__ fwdU, const float *__restrict__ fwdV,
+                                               const unsigned char *__restrict__ mask, float *__restrict__ corrU,
+                                               float *__restrict__ corrV, const float dt, const int i0, const int i1, const int j, int *bad)
+{
+    if (j >= c.NY) return;
+    const float yj = (float)j * c.h;
+    const float yj2 = yj + c.h2;
+    const int ifirst = i0 + (int)(threadIdx.x >> 7);
+    const float *pu = sU + (ifirst - vls0) * AT_PW + (j - T.cs0), *pv = sV + (ifirst - vls0) * AT_PW + (j - T.cs0);
+    size_t o = (size_t)(ifirst - c.i_alloc0) * c.pitch + j;
+    const size_t ostep = (size_t)(AT_THREADS / 128) * c.pitch;
+#pragma unroll 2
+    for (int i = ifirst; i < i1; i += AT_THREADS / 128, pu += (AT_THREADS / 128) * AT_PW, pv += (AT_THREADS / 128) * AT_PW, o += ostep) {
+        const float u = pu[0], v = pv[0];
+        float cu = u, cv = v;
+        // copy(corrU, origU) leaves the ring alone; correction and clamp run over ALL interior indices (Q-10)
+        if (FAST || (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2)) {
+            const float xi = (float)i * c.h;
+            float bwdU = 0.0f, bwdV = 0.0f;                       // bwd arrays start as zeros (fluid.go:938-939)
+            unsigned m = MK_C | MK_XM | MK_YM;
+            if (!FAST) m = mask[o];
+            if ((m & MK_C) && (m & MK_XM)) {
+                const float av = (((pv[-AT_PW] + v) + pv[-AT_PW + 1]) + pv[1]) * 0.25f;
+                const float du = dt * u, dv = dt * av;
+                bwdU = sample_tile<0, FAST, CHECK>(c, T, sFU, fwdU, xi + du, yj2 + dv, bad);
+            }
+            if ((m & MK_C) && (m & MK_YM)) {
+                const float au = (((pu[-1] + u) + pu[AT_PW - 1]) + pu[AT_PW]) * 0.25f;
+                const float du = dt * au, dv = dt * v;
+                bwdV = sample_tile<1, FAST, CHECK>(c, T, sFV, fwdV, (xi + c.h2) + du, yj + dv, bad);
+            }
+            // clampToNeighbors (fluid.go:1094-1120): min / max over the 3x3 neighbourhood of the original field
+            float loU = 3.402823466e+38f, hiU = -3.402823466e+38f, loV = 3.402823466e+38f, hiV = -3.402823466e+38f;
+#pragma unroll
+            for (int di = -1; di <= 1; di++)
+#pragma unroll
+                for (int dj = -1; dj <= 1; dj++) {
+                    const float a = pu[di * AT_PW + dj], b = pv[di * AT_PW + dj];
+                    loU = fminf(loU, a); hiU = fmaxf(hiU, a);
+                    loV = fminf(loV, b); hiV = fmaxf(hiV, b);
+                }
+            const float eu = (bwdU - u) * 0.5f;
+            const float ev = (bwdV - v) * 0.5f;
+            cu = u - eu; cv = v - ev;
+            cu = cu < loU ? loU : (cu > hiU ? hiU : cu);
+            cv = cv < loV ? loV : (cv > hiV ? hiV : cv);
+        }
+        corrU[o] = cu;
+        corrV[o] = cv;
+    }
+}
+
+template <bool CHECK>
+__global__ void __launch_bounds__(AT_THREADS)
+k_bfecc_velocity_tile(const AdvCtx c, const float *__restrict__ U, const float *__restrict__ V,
+                      const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
+                      const float *__restrict__ fwdU, const float *__restrict__ fwdV, float *__restrict__ corrU,
+                      float *__restrict__ corrV, const float dt, const int ib, const int ie, int *bad)
+{
+    extern __shared__ __align__(128) unsigned char at_smem[];
+    float *sFU = reinterpret_cast<float *>(at_smem), *sFV = sFU + AT_BTL * AT_PW;
+    float *sU = sFV + AT_BTL * AT_PW, *sV = sU + AT_BVL * AT_PW;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sV + AT_BVL * AT_PW);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ty = ib / AT_BTI + blockIdx.y;
+    const int i0 = max(ty * AT_BTI, ib), i1 = min((ty + 1) * AT_BTI, ie);
+    const int j0 = blockIdx.x * AT_TJ;
+    ATile T;
+    T.ls0 = ty * AT_BTI - (AT_R + 1); T.cs0 = j0 - AT_CH;
+    at_tile_geometry(c, T, AT_BTL);
+    const int vls0 = ty * AT_BTI - 1;
+    if (tid == 0) rq_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned b = rq_s32(bar);
+        unsigned bytes = at_stage_field(c, sFU, fwdU, T.ls0, AT_BTL, T.cs0, lane, b, false) + at_stage_field(c, sFV, fwdV, T.ls0, AT_BTL, T.cs0, lane, b, false) +
+                         at_stage_field(c, sU, U, vls0, AT_BVL, T.cs0, lane, b, false) + at_stage_field(c, sV, V, vls0, AT_BVL, T.cs0, lane, b, false);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        if (lane == 0) rq_mbar_expect_tx(bar, bytes);
+        __syncwarp();
+        at_stage_field(c, sFU, fwdU, T.ls0, AT_BTL, T.cs0, lane, b, true);
+        at_stage_field(c, sFV, fwdV, T.ls0, AT_BTL, T.cs0, lane, b, true);
+        at_stage_field(c, sU, U, vls0, AT_BVL, T.cs0, lane, b, true);
+        at_stage_field(c, sV, V, vls0, AT_BVL, T.cs0, lane, b, true);
+    }
+    // the per-tile flag refers to tiles of AT_TI lines: the flag of the AT_TI tile that contains this AT_BTI tile
+    const bool fast = T.ls0 >= 2 && T.ls0 + AT_BTL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
+                      T.ls0 >= c.i_alloc0 && T.ls0 + AT_BTL <= c.i_alloc0 + c.lines_alloc &&
+                      tile_flags[((ty * AT_BTI) / AT_TI) * ntx + blockIdx.x] != 0;
+    at_wait_tiles(bar, bad);
+    const int j = j0 + (tid & 127);
+    if (fast) at_bfecc_cells<true, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, i0, i1, j, bad);
+    else at_bfecc_cells<false, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, i0, i1, j, bad);
+}

@@ -6,6 +6,7 @@
 #include "rb_fused.cuh"
 #include "rbq_fused.cuh"
 #include "rbq_stream.cuh"
+#include "advect_tile.cuh"
 #include "multigrid.cuh"
 
 #include <cmath>
@@ -34,7 +35,9 @@ struct fb_handle {
     bool literal;                 // FB_FLAG_LITERAL: reference-shaped kernels with physical copies
     bool exact_shadow;            // FB_FLAG_EXACT_SHADOW: keep newU/newV/newM complete (white-box mode)
     bool p_zero;                  // pressure plane known to be all zero
-    bool rb_attr_set, rbq_attr_set;
+    bool rb_attr_set, rbq_attr_set, adv_tile_attr_set;
+    unsigned char *tile_flags;                          // per AT_TI x AT_TJ tile: all cells active (advect_tile.cuh)
+    int tile_ntx, tile_nty;
     bool want_stats;
     bool fuse_turb;               // apply addTurbulence in the fused solve's write-out (else its own pass)
     int nsm;
@@ -89,6 +92,11 @@ static int fail(fb_handle *h, int code, const char *what, cudaError_t e = cudaSu
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---- per-phase event timing (fb_profile_*) ----------------------------------------
+// the large kernels are timed one launch at a time as well (slots FB_PROF_K_*), inside their phase's pair
+#define PROF_SLOT_k_advect_velocity_full FB_PROF_K_ADVECT_VELOCITY
+#define PROF_SLOT_k_bfecc_velocity_correct FB_PROF_K_BFECC_VELOCITY
+#define PROF_SLOT_k_advect_smoke_full FB_PROF_K_ADVECT_SMOKE
+#define PROF_SLOT_k_bfecc_smoke_correct FB_PROF_K_BFECC_SMOKE
 struct ProfScope {
     fb_handle *h; int phase; cudaEvent_t a, b; bool on;
     static cudaEvent_t get(fb_handle *h) {
@@ -233,6 +241,7 @@ extern "C" int fb_destroy(fb_handle *h)
     for (int k = 0; k < SCR_N; k++) if (h->scr[k]) cudaFree(h->scr[k]);
     for (float *p : h->pool) cudaFree(p);
     if (h->mask) cudaFree(h->mask);
+    if (h->tile_flags) cudaFree(h->tile_flags);
     if (h->d_red) cudaFree(h->d_red);
     if (h->h_red) cudaFreeHost(h->h_red);
     if (h->d_bad) cudaFree(h->d_bad);
@@ -930,6 +939,12 @@ static int ensure_mask(fb_handle *h)
     dim3 grid, block; plane_launch(g, ib, ie, grid, block);
     k_build_mask<<<grid, block, 0, h->stream>>>(g, h->f[FB_S], h->mask, ib, ie);
     CKL("k_build_mask");
+    if (!h->tile_flags) {
+        h->tile_ntx = cdiv(g.NY, AT_TJ); h->tile_nty = cdiv(g.NX, AT_TI);
+        CK(cudaMalloc(&h->tile_flags, (size_t)h->tile_ntx * h->tile_nty));
+    }
+    k_tile_flags<<<dim3(h->tile_ntx, h->tile_nty, 1), AT_THREADS, 0, h->stream>>>(g, h->mask, h->tile_flags, h->tile_ntx);
+    CKL("k_tile_flags");
     h->mask_dirty = false;
     return FB_OK;
 }
@@ -950,10 +965,42 @@ static AdvCtx adv_ctx(const fb_handle *h)
 
 // launch helpers: CHECK (ghost-zone guard) only when the grid is split over ranks
 #define ADV_LAUNCH(kern, ...) do { \
+        ProfScope _ks(h, PROF_SLOT_##kern); \
         dim3 _grid, _block; adv_launch(h->g.NY, ib, ie, _grid, _block); \
         if (h->cfg.nranks > 1) kern<true><<<_grid, _block, 0, h->stream>>>(__VA_ARGS__); \
         else kern<false><<<_grid, _block, 0, h->stream>>>(__VA_ARGS__); \
         CKL(#kern); } while (0)
+
+// advectVelocity / the BFECC correct pass on shared-memory tiles (advect_tile.cuh); FLUIDB200_ADV_FULL=1 selects the
+// global-gather kernels of round 1 (A/B).  Arguments: (c, srcU, srcV, mask, inU, inV, outU, outV, dt, ib, ie, bad) as for
+// k_advect_velocity_full / k_bfecc_velocity_correct.
+static int adv_tile_attrs(fb_handle *h)
+{
+    if (h->adv_tile_attr_set) return FB_OK;
+    CK(cudaFuncSetAttribute(k_advect_velocity_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CK(cudaFuncSetAttribute(k_advect_velocity_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CK(cudaFuncSetAttribute(k_bfecc_velocity_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BSMEM));
+    CK(cudaFuncSetAttribute(k_bfecc_velocity_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BSMEM));
+    h->adv_tile_attr_set = true;
+    return FB_OK;
+}
+static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
+#define ADV_VELOCITY_LAUNCH(c, sU, sV, mk, aU, aV, oU, oV, dt, ib, ie, bad) do { \
+        if (adv_full) { ADV_LAUNCH(k_advect_velocity_full, c, sU, sV, mk, aU, aV, oU, oV, dt, ib, ie, bad); break; } \
+        TRY(adv_tile_attrs(h)); \
+        ProfScope _ks(h, FB_PROF_K_ADVECT_VELOCITY); \
+        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_TI) - (ib) / AT_TI, 1); \
+        if (h->cfg.nranks > 1) k_advect_velocity_tile<true><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
+        else k_advect_velocity_tile<false><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
+        CKL("k_advect_velocity_tile"); } while (0)
+#define ADV_BFECC_VELOCITY_LAUNCH(c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad) do { \
+        if (adv_full) { ADV_LAUNCH(k_bfecc_velocity_correct, c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad); break; } \
+        TRY(adv_tile_attrs(h)); \
+        ProfScope _ks(h, FB_PROF_K_BFECC_VELOCITY); \
+        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_BTI) - (ib) / AT_BTI, 1); \
+        if (h->cfg.nranks > 1) k_bfecc_velocity_tile<true><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
+        else k_bfecc_velocity_tile<false><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
+        CKL("k_bfecc_velocity_tile"); } while (0)
 
 // newX := X as the reference's copy() leaves them, only when the caller asked for it
 static int sync_shadow(fb_handle *h, int live, int shadow)
@@ -1104,6 +1151,7 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             a.noiseU = nU; a.noiseV = nV; a.turb = ts;
         }
         const size_t smem_q = rq_smem_bytes(WL, TJ);   // planes + TMA staging ring + mbarriers + progress counters
+        ProfScope _ks(h, FB_PROF_K_PRESSURE_SOLVE);
         if (!rbq_ring) {
             // fewer than 8 iterations: the trailing stages run with wd = 0 (memset above), which leaves q as it is
             if (h->want_stats) k_rbq_stream<true><<<dim3(nstrips, nchunks, 1), 64, RS_SMEM, h->stream>>>(a);
@@ -1170,6 +1218,7 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
     int ib, ie; range(h, ext, ib, ie);
     dim3 grid(cdiv(g.NY, CT_J), cdiv(ie - ib, CT_I), 1);
     volatile float ts = do_turb ? p->turbulence_strength * dt : 0.0f;
+    ProfScope _ks(h, FB_PROF_K_CONFINE_TURBULENCE);
     k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
                                                                 do_confine ? p->confinement : 0.0f, ts, ib, ie);
     CKL("k_confine_turbulence");
@@ -1186,7 +1235,7 @@ static int advect_velocity_fast(fb_handle *h, float dt, int ext = 0)
     TRY(take_plane(h, &dU)); TRY(take_plane(h, &dV));
     int ib, ie; range(h, ext, ib, ie);
     const AdvCtx c = adv_ctx(h);
-    ADV_LAUNCH(k_advect_velocity_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], dU, dV, dt, ib, ie, h->d_bad);
+    ADV_VELOCITY_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], dU, dV, dt, ib, ie, h->d_bad);
     give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
     h->f[FB_U] = dU; h->f[FB_V] = dV;
     TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
@@ -1217,15 +1266,15 @@ static int advect_velocity_bfecc_fast(fb_handle *h, float dt, int ext_fwd = 0, i
     int ib, ie; range(h, ext_fwd, ib, ie);
     const AdvCtx c = adv_ctx(h);
     // pass 1: forward advection of the original field
-    ADV_LAUNCH(k_advect_velocity_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], fU, fV, dt, ib, ie, h->d_bad);
+    ADV_VELOCITY_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_NEWU], h->f[FB_NEWV], fU, fV, dt, ib, ie, h->d_bad);
     // pass 2: back-trace through the original velocities + compensation + clamp
     range(h, ext_corr, ib, ie);
-    ADV_LAUNCH(k_bfecc_velocity_correct, c, h->f[FB_U], h->f[FB_V], h->mask, fU, fV, cU, cV, dt, ib, ie, h->d_bad);
+    ADV_BFECC_VELOCITY_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, fU, fV, cU, cV, dt, ib, ie, h->d_bad);
     // pass 3: the corrected field advects itself; skipped faces keep the stale scratch
     // value, which after pass 1 is the forward result there == the old scratch value
     float *oU = h->f[FB_U], *oV = h->f[FB_V];
     range(h, ext_final, ib, ie);
-    ADV_LAUNCH(k_advect_velocity_full, c, cU, cV, h->mask, h->f[FB_NEWU], h->f[FB_NEWV], oU, oV, dt, ib, ie, h->d_bad);
+    ADV_VELOCITY_LAUNCH(c, cU, cV, h->mask, h->f[FB_NEWU], h->f[FB_NEWV], oU, oV, dt, ib, ie, h->d_bad);
     give_plane(h, fU); give_plane(h, fV); give_plane(h, cU); give_plane(h, cV);
     TRY(sync_shadow(h, FB_U, FB_NEWU)); TRY(sync_shadow(h, FB_V, FB_NEWV));
     return FB_OK;

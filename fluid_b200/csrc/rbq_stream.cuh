@@ -79,7 +79,7 @@ static_assert(2 * RS_HS == RQ_NIT, "two warps share the iterations of a pass");
 __device__ __forceinline__ void rs_wait(unsigned bar, unsigned parity, int *debug, int tag)
 {
 #pragma unroll 1
-    for (int k = 0; k < (1 << 22); k++)
+    for (int k = 0; k < (1 << 17); k++)      // try_wait suspends the warp for up to ~microseconds per poll: well under a second in all
         if (rq_mbar_try_a(bar, parity)) return;
     // a TMA that never lands must not hang the GPU: latch a record, fall through (the host returns FB_ERR_CUDA)
     if (debug && atomicCAS(debug, 0, 1) == 0) {
@@ -286,7 +286,7 @@ __device__ __forceinline__ void rs_tick(const RSK &K, const RSIO &Q, const RBQ &
         rs_bar_arrive(1 + qs);
         // ---------------- loader: staged line LL = k + 1 -> -D0, neighbour counts ----------------
         const int LL = k + 1;
-        if (LL >= 0) {
+        if (LL >= 0 && LL < K.nproc) {      // the loop's last (odd) tick may lie one past the last line
             const int st0 = LL & (RS_LST - 1), st1 = (LL + 1) & (RS_LST - 1);
             rs_wait(Q.b_full + 8u * (unsigned)st0, (unsigned)(LL / RS_LST) & 1u, Q.debug, (30 << 20) | LL);
             rs_wait(Q.b_full + 8u * (unsigned)st1, (unsigned)((LL + 1) / RS_LST) & 1u, Q.debug, (31 << 20) | LL);

@@ -274,6 +274,10 @@ int fb_timer_stop(fb_handle *h, float *elapsed_ms);
 typedef enum fb_prof_phase {
     FB_PROF_EDITS = 0, FB_PROF_CLEAR_PRESSURE, FB_PROF_VISCOSITY, FB_PROF_PROJECT, FB_PROF_CONFINEMENT,
     FB_PROF_TURBULENCE, FB_PROF_BORDERS, FB_PROF_ADVECT_VELOCITY, FB_PROF_ADVECT_SMOKE,
+    /* single kernels, one pair per launch (they lie inside the phase pairs above): the fused pressure solve, the
+     * semi-Lagrangian passes (k_advect_*_full), the BFECC back-trace + correct passes, confinement + turbulence */
+    FB_PROF_K_PRESSURE_SOLVE, FB_PROF_K_ADVECT_VELOCITY, FB_PROF_K_BFECC_VELOCITY, FB_PROF_K_ADVECT_SMOKE,
+    FB_PROF_K_BFECC_SMOKE, FB_PROF_K_CONFINE_TURBULENCE,
     FB_PROF_NPHASES
 } fb_prof_phase;
 int fb_profile_enable(fb_handle *h, int32_t on);
