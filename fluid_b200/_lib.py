@@ -82,6 +82,7 @@ SYMBOLS = {
     "fb_halo_exchange": (C.c_int, [_H]),
     "fb_view_begin": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "fb_view_end": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "fb_view_u8_begin": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fb_render_begin": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]),
     "fb_render_end": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fb_render": (C.c_int, [_H, C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -89,9 +89,10 @@ __device__ __forceinline__ float sample_tile(const AdvCtx &c, const ATile &T, co
     const float ys = (FLD == 1) ? yc : yc - c.h2;
     const float2 s2 = make_float2(xs, ys), h1 = make_float2(c.h1, c.h1);
     const float2 q = __fmul2_rn(s2, h1);
-    const float fx = floorf(q.x), fy = floorf(q.y);
-    const int x0 = (int)fx, y0 = (int)fy;
+    // floor as ONE conversion (F2I.FLOOR); inside the staged region |q| is small, so float(x0) IS floorf(q.x)
+    const int x0 = __float2int_rd(q.x), y0 = __float2int_rd(q.y);
     if ((unsigned)(x0 - T.vl0) < T.nl && (unsigned)(y0 - T.vc0) < T.nc) {
+        const float fx = (float)x0, fy = (float)y0;
         const float2 f0h = __fmul2_rn(make_float2(fx, fy), make_float2(c.h, c.h));
         const float2 t = __fmul2_rn(__fadd2_rn(s2, make_float2(-f0h.x, -f0h.y)), h1);
         const float2 sxy = __fadd2_rn(make_float2(1.0f, 1.0f), make_float2(-t.x, -t.y));
@@ -136,12 +137,16 @@ __device__ __forceinline__ void at_tile_geometry(const AdvCtx &c, ATile &T, cons
 
 __device__ __forceinline__ void at_wait_tiles(unsigned long long *bar, int *bad)
 {
-    // every thread waits for the tiles (bounded: a copy that never lands latches the error flag instead of hanging)
-    const unsigned b = rq_s32(bar);
-    bool ok = false;
+    // ONE warp waits for the tiles, the others sleep in the block barrier: polling by all eight warps cost 22 % of
+    // the kernel's issued instructions (ncu, round 2).  Bounded: a copy that never lands latches the error flag.
+    if (threadIdx.x < 32) {
+        const unsigned b = rq_s32(bar);
+        bool ok = false;
 #pragma unroll 1
-    for (int k = 0; k < (1 << 17) && !ok; k++) ok = rq_mbar_try_a(b, 0);
-    if (!ok && bad) *bad = 3;
+        for (int k = 0; k < (1 << 17) && !ok; k++) ok = rq_mbar_try_a(b, 0);
+        if (!ok && bad) *bad = 3;
+    }
+    __syncthreads();
 }
 
 // FAST: the tile is interior (no coordinate clamps) and all its cells are active (flag of k_tile_flags): every face is
@@ -156,18 +161,24 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
     if (j >= c.NY) return;
     const float yj = (float)j * c.h;
     const float yj2 = yj + c.h2;
-    const int ifirst = i0 + (int)(threadIdx.x >> 7);
-    const float *pu = sU + (ifirst - T.ls0) * AT_PW + (j - T.cs0), *pv = sV + (ifirst - T.ls0) * AT_PW + (j - T.cs0);
-    size_t o = (size_t)(ifirst - c.i_alloc0) * c.pitch + j;
-    const size_t ostep = (size_t)(AT_THREADS / 128) * c.pitch;
+    // a thread walks CONSECUTIVE lines of its column: half of the CTA takes the first AT_TI / 2 lines, half the rest.
+    // Of the eight values the two averages need, four are the previous line's (carried), four are new
+    const int half = AT_TI / (AT_THREADS / 128);
+    const int ia = i0 + (int)(threadIdx.x >> 7) * half, ib = min(ia + half, i1);
+    if (ia >= ib) return;
+    const float *pu = sU + (ia - T.ls0) * AT_PW + (j - T.cs0), *pv = sV + (ia - T.ls0) * AT_PW + (j - T.cs0);
+    size_t o = (size_t)(ia - c.i_alloc0) * c.pitch + j;
+    float um = pu[-1], u = pu[0];                  // U[i, j-1], U[i, j]
+    float vm0 = pv[-AT_PW], vm1 = pv[-AT_PW + 1];  // V[i-1, j], V[i-1, j+1]
 #pragma unroll 2
-    for (int i = ifirst; i < i1; i += AT_THREADS / 128, pu += (AT_THREADS / 128) * AT_PW, pv += (AT_THREADS / 128) * AT_PW, o += ostep) {
-        const float u = pu[0], v = pv[0];
+    for (int i = ia; i < ib; i++, pu += AT_PW, pv += AT_PW, o += c.pitch) {
+        const float upm = pu[AT_PW - 1], up = pu[AT_PW];      // U[i+1, j-1], U[i+1, j]
+        const float v = pv[0], vn = pv[1];                    // V[i, j], V[i, j+1]
         const float xi = (float)i * c.h;
         float outU, outV;
         if (FAST) {
-            const float av = (((pv[-AT_PW] + v) + pv[-AT_PW + 1]) + pv[1]) * 0.25f;        // avgV (fluid.go:342-347)
-            const float au = (((pu[-1] + u) + pu[AT_PW - 1]) + pu[AT_PW]) * 0.25f;         // avgU (fluid.go:335-340)
+            const float av = (((vm0 + v) + vm1) + vn) * 0.25f;        // avgV (fluid.go:342-347)
+            const float au = (((um + u) + upm) + up) * 0.25f;         // avgU (fluid.go:335-340)
             const float du = dt * u, dv = dt * av;
             outU = sample_tile<0, true, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
             const float du2 = dt * au, dv2 = dt * v;
@@ -180,7 +191,7 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
             const bool ring = i == 0 || j == 0 || i == c.NX - 1 || j == c.NY - 1;
             if (act_u) {
                 // avgV (fluid.go:342-347): V[i-1,j] + V[i,j] + V[i-1,j+1] + V[i,j+1]
-                const float av = (((pv[-AT_PW] + v) + pv[-AT_PW + 1]) + pv[1]) * 0.25f;
+                const float av = (((vm0 + v) + vm1) + vn) * 0.25f;
                 const float du = dt * u, dv = dt * av;
                 outU = sample_tile<0, false, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
             } else {
@@ -188,7 +199,7 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
             }
             if (act_v) {
                 // avgU (fluid.go:335-340): U[i,j-1] + U[i,j] + U[i+1,j-1] + U[i+1,j]
-                const float au = (((pu[-1] + u) + pu[AT_PW - 1]) + pu[AT_PW]) * 0.25f;
+                const float au = (((um + u) + upm) + up) * 0.25f;
                 const float du = dt * au, dv = dt * v;
                 outV = sample_tile<1, false, CHECK>(c, T, sV, trV, (xi + c.h2) - du, yj - dv, bad);
             } else {
@@ -197,6 +208,7 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
         }
         dstU[o] = outU;
         dstV[o] = outV;
+        um = upm; u = up; vm0 = v; vm1 = vn;
     }
 }
 
@@ -204,7 +216,7 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
 // through AND sampled; sh*: the stale scratch values skipped faces fall back to, Q-6).  blockIdx.y counts tiles from
 // the one that holds line ib.
 template <bool CHECK>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, 4)
 k_advect_velocity_tile(const AdvCtx c, const float *__restrict__ trU, const float *__restrict__ trV,
                        const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
                        const float *__restrict__ shU, const float *__restrict__ shV, float *__restrict__ dstU,
@@ -255,13 +267,19 @@ __device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, 
     if (j >= c.NY) return;
     const float yj = (float)j * c.h;
     const float yj2 = yj + c.h2;
-    const int ifirst = i0 + (int)(threadIdx.x >> 7);
-    const float *pu = sU + (ifirst - vls0) * AT_PW + (j - T.cs0), *pv = sV + (ifirst - vls0) * AT_PW + (j - T.cs0);
-    size_t o = (size_t)(ifirst - c.i_alloc0) * c.pitch + j;
-    const size_t ostep = (size_t)(AT_THREADS / 128) * c.pitch;
+    // consecutive lines per thread: the 3x3 windows of U and V slide down one line per cell, two rows are carried
+    const int half = AT_BTI / (AT_THREADS / 128);
+    const int ia = i0 + (int)(threadIdx.x >> 7) * half, ib = min(ia + half, i1);
+    if (ia >= ib) return;
+    const float *pu = sU + (ia - vls0) * AT_PW + (j - T.cs0), *pv = sV + (ia - vls0) * AT_PW + (j - T.cs0);
+    size_t o = (size_t)(ia - c.i_alloc0) * c.pitch + j;
+    float ua[3] = { pu[-AT_PW - 1], pu[-AT_PW], pu[-AT_PW + 1] }, ub[3] = { pu[-1], pu[0], pu[1] };      // rows i-1, i of U
+    float va[3] = { pv[-AT_PW - 1], pv[-AT_PW], pv[-AT_PW + 1] }, vb[3] = { pv[-1], pv[0], pv[1] };
 #pragma unroll 2
-    for (int i = ifirst; i < i1; i += AT_THREADS / 128, pu += (AT_THREADS / 128) * AT_PW, pv += (AT_THREADS / 128) * AT_PW, o += ostep) {
-        const float u = pu[0], v = pv[0];
+    for (int i = ia; i < ib; i++, pu += AT_PW, pv += AT_PW, o += c.pitch) {
+        const float uc[3] = { pu[AT_PW - 1], pu[AT_PW], pu[AT_PW + 1] };                                  // row i+1
+        const float vc[3] = { pv[AT_PW - 1], pv[AT_PW], pv[AT_PW + 1] };
+        const float u = ub[1], v = vb[1];
         float cu = u, cv = v;
         // copy(corrU, origU) leaves the ring alone; correction and clamp run over ALL interior indices (Q-10)
         if (FAST || (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2)) {
@@ -270,25 +288,23 @@ __device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, 
             unsigned m = MK_C | MK_XM | MK_YM;
             if (!FAST) m = mask[o];
             if ((m & MK_C) && (m & MK_XM)) {
-                const float av = (((pv[-AT_PW] + v) + pv[-AT_PW + 1]) + pv[1]) * 0.25f;
+                const float av = (((va[1] + v) + va[2]) + vb[2]) * 0.25f;          // V[i-1,j] + V[i,j] + V[i-1,j+1] + V[i,j+1]
                 const float du = dt * u, dv = dt * av;
                 bwdU = sample_tile<0, FAST, CHECK>(c, T, sFU, fwdU, xi + du, yj2 + dv, bad);
             }
             if ((m & MK_C) && (m & MK_YM)) {
-                const float au = (((pu[-1] + u) + pu[AT_PW - 1]) + pu[AT_PW]) * 0.25f;
+                const float au = (((ub[0] + u) + uc[0]) + uc[1]) * 0.25f;          // U[i,j-1] + U[i,j] + U[i+1,j-1] + U[i+1,j]
                 const float du = dt * au, dv = dt * v;
                 bwdV = sample_tile<1, FAST, CHECK>(c, T, sFV, fwdV, (xi + c.h2) + du, yj + dv, bad);
             }
             // clampToNeighbors (fluid.go:1094-1120): min / max over the 3x3 neighbourhood of the original field
-            float loU = 3.402823466e+38f, hiU = -3.402823466e+38f, loV = 3.402823466e+38f, hiV = -3.402823466e+38f;
+            float loU = fminf(fminf(ua[0], ua[1]), ua[2]), hiU = fmaxf(fmaxf(ua[0], ua[1]), ua[2]);
+            float loV = fminf(fminf(va[0], va[1]), va[2]), hiV = fmaxf(fmaxf(va[0], va[1]), va[2]);
 #pragma unroll
-            for (int di = -1; di <= 1; di++)
-#pragma unroll
-                for (int dj = -1; dj <= 1; dj++) {
-                    const float a = pu[di * AT_PW + dj], b = pv[di * AT_PW + dj];
-                    loU = fminf(loU, a); hiU = fmaxf(hiU, a);
-                    loV = fminf(loV, b); hiV = fmaxf(hiV, b);
-                }
+            for (int q = 0; q < 3; q++) {
+                loU = fminf(fminf(loU, ub[q]), uc[q]); hiU = fmaxf(fmaxf(hiU, ub[q]), uc[q]);
+                loV = fminf(fminf(loV, vb[q]), vc[q]); hiV = fmaxf(fmaxf(hiV, vb[q]), vc[q]);
+            }
             const float eu = (bwdU - u) * 0.5f;
             const float ev = (bwdV - v) * 0.5f;
             cu = u - eu; cv = v - ev;
@@ -297,11 +313,13 @@ __device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, 
         }
         corrU[o] = cu;
         corrV[o] = cv;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { ua[q] = ub[q]; ub[q] = uc[q]; va[q] = vb[q]; vb[q] = vc[q]; }
     }
 }
 
 template <bool CHECK>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, 4)
 k_bfecc_velocity_tile(const AdvCtx c, const float *__restrict__ U, const float *__restrict__ V,
                       const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
                       const float *__restrict__ fwdU, const float *__restrict__ fwdV, float *__restrict__ corrU,

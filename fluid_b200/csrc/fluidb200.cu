@@ -1154,8 +1154,8 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         ProfScope _ks(h, FB_PROF_K_PRESSURE_SOLVE);
         if (!rbq_ring) {
             // fewer than 8 iterations: the trailing stages run with wd = 0 (memset above), which leaves q as it is
-            if (h->want_stats) k_rbq_stream<true><<<dim3(nstrips, nchunks, 1), 64, RS_SMEM, h->stream>>>(a);
-            else k_rbq_stream<false><<<dim3(nstrips, nchunks, 1), 64, RS_SMEM, h->stream>>>(a);
+            if (h->want_stats) k_rbq_stream<true><<<dim3(nstrips, nchunks, 1), RS_THREADS, RS_SMEM, h->stream>>>(a);
+            else k_rbq_stream<false><<<dim3(nstrips, nchunks, 1), RS_THREADS, RS_SMEM, h->stream>>>(a);
             CKL("k_rbq_stream");
         } else {
             if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
@@ -1760,6 +1760,69 @@ extern "C" int fb_view_begin(fb_handle *h, int32_t kind, float *out)
     CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaEventRecord(h->ev_view, h->copy_stream));
     // the next kernel that touches d_red[32..33] or the snapshot is the next fb_view_begin, after fb_view_end
+    h->view_in_flight = true;
+    return FB_OK;
+}
+
+// Decimated 8-bit pipelined view: the full-field min / max reduction of `kind`, then every stride-th cell of every
+// stride-th line quantised against it on the device (k_quantize_u8); what travels is ceil(lines/stride) x ceil(NumY/stride)
+// BYTES instead of lines x NumY floats.  Same begin / end protocol and in-flight slot as fb_view_begin.
+extern "C" int fb_view_u8_begin(fb_handle *h, int32_t kind, int32_t stride, uint8_t *out, int32_t *out_lines, int32_t *out_cols)
+{
+    if (!h || !out || stride < 1) return FB_ERR_INVALID;
+    if (h->view_in_flight) return fail(h, FB_ERR_INVALID, "fb_view_u8_begin: a view is already in flight");
+    CK(cudaSetDevice(h->device));
+    const Grid &g = h->g;
+    int ib, ie; range(h, 0, ib, ie);
+    dim3 grid, block; plane_launch(g, ib, ie, grid, block);
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_view, cudaEventDisableTiming));
+    }
+    float *snap;
+    TRY(scratch(h, SCR_SNAP, &snap));
+    k_minmax_init<<<1, 1, 0, h->stream>>>(h->d_red + 32);
+    CKL("k_minmax_init");
+    const float *src = nullptr;
+    switch (kind) {
+    case FB_VIEW_SMOKE: src = h->f[FB_M]; break;
+    case FB_VIEW_PRESSURE: src = h->f[FB_P]; break;
+    case FB_VIEW_VELOCITY_MAGNITUDE: case FB_VIEW_VORTICITY: {
+        float *view;
+        TRY(scratch(h, SCR_VIEW, &view));
+        if (kind == FB_VIEW_VORTICITY)
+            k_view<FB_VIEW_VORTICITY><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        else
+            k_view<FB_VIEW_VELOCITY_MAGNITUDE><<<grid, block, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->f[FB_S], view, h->cfg.h, h->d_red + 32, ib, ie);
+        CKL("k_view");
+        src = view;
+        break;
+    }
+    default: return fail(h, FB_ERR_INVALID, "unknown view");
+    }
+    if (kind == FB_VIEW_SMOKE || kind == FB_VIEW_PRESSURE) {
+        k_minmax_all<<<grid, block, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
+        CKL("k_minmax_all");
+    }
+    // owned lines whose global index is a multiple of stride: oi0 .. oi0 + ni - 1 (in units of stride)
+    const int oi0 = cdiv(ib, stride), ni = cdiv(ie, stride) - oi0, nj = cdiv(g.NY, stride);
+    if (ni > 0) {
+        unsigned char *q = reinterpret_cast<unsigned char *>(snap);
+        const dim3 qb(32, 8, 1), qg(cdiv(nj, 32), cdiv(ni, 8), 1);
+        k_quantize_u8<<<qg, qb, 0, h->stream>>>(g, src, q, h->d_red + 32, stride, oi0, ni, nj);
+        CKL("k_quantize_u8");
+        CK(cudaEventRecord(h->ev_snap, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+        CK(cudaMemcpyAsync(out, q, (size_t)ni * nj, cudaMemcpyDeviceToHost, h->copy_stream));
+    } else {
+        CK(cudaEventRecord(h->ev_snap, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    }
+    CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(h->ev_view, h->copy_stream));
+    if (out_lines) *out_lines = ni > 0 ? ni : 0;
+    if (out_cols) *out_cols = nj;
     h->view_in_flight = true;
     return FB_OK;
 }

@@ -620,6 +620,25 @@ __global__ void k_snapshot_minmax(Grid g, const float *__restrict__ A, float *__
     if (reduce) block_minmax(lo, hi, red);
 }
 
+// Decimated 8-bit view for frame loops whose field is larger than any display: every `stride`-th cell of every
+// `stride`-th line (global indices that are multiples of stride), quantised against the min / max the reduction of the
+// SAME queue left in red[0..1]: index = (unsigned)(min(max((v - lo) * (255 / (hi - lo)), 0), 255) + 0.5).  The host maps
+// the index through a 256-entry table of the UI's colormap (main/colors.go).  out[(i/stride - ob) * nj + j/stride].
+__device__ __forceinline__ float key2f_dev_(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__global__ void k_quantize_u8(Grid g, const float *__restrict__ A, unsigned char *__restrict__ out, const unsigned *__restrict__ red,
+                              int stride, int oi0, int ni, int nj)
+{
+    const int jo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int io = blockIdx.y * blockDim.y + threadIdx.y;
+    if (io >= ni || jo >= nj) return;
+    const float lo = key2f_dev_(red[0]), hi = key2f_dev_(red[1]);
+    const float range = hi - lo;
+    const float scale = range > 0.0f ? 255.0f / range : 0.0f;
+    const float v = A[g.at((oi0 + io) * stride, jo * stride)];
+    const float q = fminf(fmaxf((v - lo) * scale, 0.0f), 255.0f) + 0.5f;
+    out[(size_t)io * nj + jo] = (unsigned char)(unsigned)q;
+}
+
 // Vorticity (fluid.go:806-838) / VelocityMagnitude (fluid.go:841-873)
 template <int KIND>
 __global__ void k_view(Grid g, const float *__restrict__ U, const float *__restrict__ V,

@@ -174,9 +174,9 @@ __device__ __forceinline__ bool rq_mbar_try_a(unsigned bar, unsigned parity)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"      // %3: suspend-time hint (ns): the warp may sleep that long per poll
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x4000u) : "memory");
     return ok != 0;
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier

@@ -359,8 +359,18 @@ class Fluid:
         addr = out if isinstance(out, int) else out.ctypes.data
         L.check(self._h, L.lib.fb_view_begin(self._h, kind, addr))
 
+    def view_u8_begin(self, kind: int, stride: int, out):
+        """Pipelined decimated 8-bit view (fb_view_u8_begin): every ``stride``-th cell of every ``stride``-th line,
+        quantised on the device against the full field's min / max; ``out`` is a pinned uint8 host array (or its
+        address) of at least ceil(lines/stride) * ceil(NumY/stride) bytes.  Returns (lines, cols); pair with view_end()."""
+        self.flush()
+        addr = out if isinstance(out, int) else out.ctypes.data
+        nl, nc = C.c_int32(), C.c_int32()
+        L.check(self._h, L.lib.fb_view_u8_begin(self._h, kind, stride, addr, C.byref(nl), C.byref(nc)))
+        return nl.value, nc.value
+
     def view_end(self):
-        """Wait for the view started by view_begin(); returns (min, max)."""
+        """Wait for the view started by view_begin() / view_u8_begin(); returns (min, max)."""
         mn, mx = C.c_float(), C.c_float()
         L.check(self._h, L.lib.fb_view_end(self._h, C.byref(mn), C.byref(mx)))
         return mn.value, mx.value

@@ -210,6 +210,14 @@ int fb_view(fb_handle *h, int32_t kind, float *out_or_null, float *min_value, fl
  * main/main.go's draw-frame-k-while-computing-k+1 loop: Smoke() at main/main.go:247. */
 int fb_view_begin(fb_handle *h, int32_t kind, float *out);
 int fb_view_end(fb_handle *h, float *min_value, float *max_value);
+/* The same pipelined view, decimated and quantised for frame loops whose field is larger than any display (and for N
+ * GPUs sharing one host's PCIe): min / max over the FULL field as above, then every stride-th cell of every stride-th
+ * line (global indices that are multiples of stride) as one byte,
+ *   index = (unsigned)(min(max((v - min) * (255 / (max - min)), 0), 255) + 0.5)      (0 when max == min),
+ * written densely to `out` as [out_lines][out_cols] (this rank's lines only; pinned host memory).  The caller maps the
+ * index through a 256-entry table of main/colors.go's palette.  Ends with fb_view_end.  The full-field float path
+ * (fb_view / fb_view_begin) stays the parity path. */
+int fb_view_u8_begin(fb_handle *h, int32_t kind, int32_t stride, uint8_t *out, int32_t *out_lines, int32_t *out_cols);
 /* ---- the frame loop either side of Simulate: Draw's pixel pass and advectParticles ---------
  * fb_render*: the view through the UI's colormap (main/colors.go:8-84: getSciValue; getDivergingColor
  * for vorticity) with solid cells black (main/main.go:564-574), as the RGBA image Draw hands to the

@@ -348,6 +348,32 @@ def test_pipelined_view_equals_blocking_view_and_overlaps_next_step():
     g.close()
 
 
+@pytest.mark.parametrize("stride", [1, 3, 4])
+def test_decimated_u8_view_is_the_quantised_full_view(stride):
+    """fb_view_u8_begin / fb_view_end: min / max equal the full view's, and every byte is the stated quantisation
+    (float32, no FMA) of the cell it samples -- the frame-loop view for fields larger than a display."""
+    from fluid_b200 import _lib as L
+    from fluid_b200 import presets
+    p = presets.karman(150, 90)
+    o = developed_state(p)
+    g = gpu_clone(o, p)
+    for kind in (L.VIEW_SMOKE, L.VIEW_PRESSURE, L.VIEW_VELOCITY_MAGNITUDE, L.VIEW_VORTICITY):
+        full = np.zeros((g.NumX, g.NumY), dtype=np.float32)
+        g.view_begin(kind, full)
+        mn, mx = g.view_end()
+        ni, nj = -(-g.NumX // stride), -(-g.NumY // stride)
+        out = np.zeros(ni * nj + 64, dtype=np.uint8)
+        got = g.view_u8_begin(kind, stride, out)
+        mn8, mx8 = g.view_end()
+        assert got == (ni, nj) and (mn8, mx8) == (mn, mx)
+        lo, hi = np.float32(mn), np.float32(mx)
+        scale = np.float32(255.0) / (hi - lo) if hi > lo else np.float32(0.0)
+        v = full[::stride, ::stride]
+        want = (np.minimum(np.maximum((v - lo) * scale, np.float32(0.0)), np.float32(255.0)) + np.float32(0.5)).astype(np.uint32)
+        assert np.array_equal(out[:ni * nj].reshape(ni, nj), want.astype(np.uint8)), kind
+    g.close()
+
+
 @pytest.mark.parametrize("preset_name", ["karman", "cavity"])
 def test_render_matches_the_ui_pixel_pass(preset_name):
     """fb_render == Draw's pixel pass (main/main.go:550-574, 620-652; main/colors.go) restated in the oracle:
