@@ -943,7 +943,7 @@ static int ensure_mask(fb_handle *h)
         h->tile_ntx = cdiv(g.NY, AT_TJ); h->tile_nty = cdiv(g.NX, AT_TI);
         CK(cudaMalloc(&h->tile_flags, (size_t)h->tile_ntx * h->tile_nty));
     }
-    k_tile_flags<<<dim3(h->tile_ntx, h->tile_nty, 1), AT_THREADS, 0, h->stream>>>(g, h->mask, h->tile_flags, h->tile_ntx);
+    k_tile_flags<<<dim3(h->tile_ntx, h->tile_nty, 1), 256, 0, h->stream>>>(g, h->mask, h->tile_flags, h->tile_ntx);
     CKL("k_tile_flags");
     h->mask_dirty = false;
     return FB_OK;
@@ -989,7 +989,8 @@ static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
         if (adv_full) { ADV_LAUNCH(k_advect_velocity_full, c, sU, sV, mk, aU, aV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
         ProfScope _ks(h, FB_PROF_K_ADVECT_VELOCITY); \
-        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_TI) - (ib) / AT_TI, 1); \
+        const int _nt = h->tile_ntx * (cdiv(ie, AT_TI) - (ib) / AT_TI); \
+        const dim3 _grid(_nt < 2 * h->nsm ? _nt : 2 * h->nsm, 1, 1); \
         if (h->cfg.nranks > 1) k_advect_velocity_tile<true><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         else k_advect_velocity_tile<false><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         CKL("k_advect_velocity_tile"); } while (0)
@@ -997,7 +998,8 @@ static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
         if (adv_full) { ADV_LAUNCH(k_bfecc_velocity_correct, c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
         ProfScope _ks(h, FB_PROF_K_BFECC_VELOCITY); \
-        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_BTI) - (ib) / AT_BTI, 1); \
+        const int _nt = h->tile_ntx * (cdiv(ie, AT_BTI) - (ib) / AT_BTI); \
+        const dim3 _grid(_nt < 2 * h->nsm ? _nt : 2 * h->nsm, 1, 1); \
         if (h->cfg.nranks > 1) k_bfecc_velocity_tile<true><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
         else k_bfecc_velocity_tile<false><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
         CKL("k_bfecc_velocity_tile"); } while (0)

@@ -168,15 +168,27 @@ __device__ __forceinline__ void rq_arrive_a(unsigned bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef RQ_TRYWAIT_HINT
+#define RQ_TRYWAIT_HINT 0x4000      // ns a waiting warp may sleep per poll (0: no hint, the hardware default)
+#endif
 __device__ __forceinline__ bool rq_mbar_try_a(unsigned bar, unsigned parity)
 {
     unsigned ok;
+#if RQ_TRYWAIT_HINT
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"      // %3: suspend-time hint (ns): the warp may sleep that long per poll
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x4000u) : "memory");
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"((unsigned)RQ_TRYWAIT_HINT) : "memory");
+#else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
