@@ -17,8 +17,10 @@
 //   * a per-tile flag built with the neighbour mask (k_tile_flags: every cell of the tile is an interior fluid cell
 //     with fluid on its -x and -y side) selects a straight-line body without the active / ring / stale-scratch cases
 //     of fluid.go:300-317 -- all of a preset's domain except walls and obstacles;
-//   * CTAs are persistent (two per SM) and double-buffered: tile n+1 of a CTA's list streams in while tile n is computed
-//     (with one buffer and four CTAs per SM 30-45 % of the stall samples sat at the barrier behind the tile load);
+//   * one tile per CTA, four CTAs per SM: the tile load of one CTA hides behind the arithmetic of the others.  Measured and
+//     NOT adopted: persistent CTAs (two per SM, 512 threads) with two buffers, the next tile streaming in while this one is
+//     computed -- 0.127 / 0.217 ms against 0.097 / 0.154 for the two kernels at 4098^2: the block-wide barrier per tile
+//     idles half of an SM's warps, whereas four independent CTAs never wait for each other;
 //   * a trace that leaves the staged region (|dt*u| > AT_R cells, or the domain edge) falls back to the global
 //     sampler sample_fast<> on the ORIGINAL coordinates, out of line: same result, slower, rare.
 // The arithmetic per face is the reference's, operation for operation (same code as sample_fast).
@@ -37,11 +39,14 @@
 #define AT_PW (AT_TJ + 2 * AT_CH)        // staged columns: 144
 #define AT_TL (AT_TI + 2 * (AT_R + 1))   // staged lines of a sampled plane
 #ifndef AT_THREADS
-#define AT_THREADS 512        // four line groups x 128 columns; a thread walks AT_TI / 4 consecutive lines of its column
+#define AT_THREADS 256        // two line groups x 128 columns; a thread walks AT_TI / 2 consecutive lines of its column
+#endif
+#ifndef AT_MINB
+#define AT_MINB 4             // CTAs per SM the kernels are compiled for
 #endif
 #define AT_LG (AT_THREADS / 128)
-#define AT_BUF (2 * AT_TL * AT_PW * 4)            // one tile buffer: U and V
-#define AT_SMEM (2 * AT_BUF + 16)                 // two buffers (the next tile loads while this one is computed) + 2 mbarriers
+#define AT_BUF (2 * AT_TL * AT_PW * 4)            // the tile buffer: U and V
+#define AT_SMEM (AT_BUF + 16)
 // BFECC correct: U, V with a one-line halo (trace velocities, 3x3 clamp) + fwdU, fwdV with the full halo
 #ifndef AT_BTI
 #define AT_BTI 16
@@ -49,7 +54,7 @@
 #define AT_BTL (AT_BTI + 2 * (AT_R + 1))
 #define AT_BVL (AT_BTI + 2)
 #define AT_BBUF ((2 * AT_BTL + 2 * AT_BVL) * AT_PW * 4)
-#define AT_BSMEM (2 * AT_BBUF + 16)
+#define AT_BSMEM (AT_BBUF + 16)
 static_assert(AT_CH >= AT_R + 1 && AT_CH % 4 == 0, "column halo");
 static_assert(AT_TI % AT_BTI == 0, "a BFECC tile lies inside one flag tile");
 
@@ -220,56 +225,45 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
 }
 
 // advectVelocity writing complete planes: same contract as k_advect_velocity_full (tr*: the planes that are traced
-// through AND sampled; sh*: the stale scratch values skipped faces fall back to, Q-6).  Persistent: CTA b takes the
-// tiles b, b + gridDim.x, ... of the ntx x nty tiles that cover lines [ib, ie) (line tile ty0 holds line ib).
+// through AND sampled; sh*: the stale scratch values skipped faces fall back to, Q-6).  blockIdx.y counts line tiles from
+// the one that holds line ib.
 template <bool CHECK>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, AT_MINB)
 k_advect_velocity_tile(const AdvCtx c, const float *__restrict__ trU, const float *__restrict__ trV,
                        const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
                        const float *__restrict__ shU, const float *__restrict__ shV, float *__restrict__ dstU,
                        float *__restrict__ dstV, const float dt, const int ib, const int ie, int *bad)
 {
     extern __shared__ __align__(128) unsigned char at_smem[];
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(at_smem + 2 * AT_BUF);
+    float *sU = reinterpret_cast<float *>(at_smem), *sV = sU + AT_TL * AT_PW;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(at_smem + AT_BUF);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int ty0 = ib / AT_TI, ntiles = ntx * (cdiv_dev(ie, AT_TI) - ty0);
-    if (tid == 0) { rq_mbar_init(bars, 1); rq_mbar_init(bars + 1, 1); }
+    const int ty = ib / AT_TI + blockIdx.y, tx = blockIdx.x;
+    const int i0 = max(ty * AT_TI, ib), i1 = min((ty + 1) * AT_TI, ie);
+    ATile T;
+    T.ls0 = ty * AT_TI - (AT_R + 1); T.cs0 = tx * AT_TJ - AT_CH;
+    at_tile_geometry(c, T, AT_TL);
+    if (tid == 0) rq_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    auto stage = [&](const int n, const int buf) {            // warp 0: tile n -> buffer buf
-        float *sU = reinterpret_cast<float *>(at_smem + buf * AT_BUF), *sV = sU + AT_TL * AT_PW;
-        const int ls0 = (ty0 + n / ntx) * AT_TI - (AT_R + 1), cs0 = (n % ntx) * AT_TJ - AT_CH;
-        const unsigned b = rq_s32(bars + buf);
-        unsigned bytes = at_stage_field(c, sU, trU, ls0, AT_TL, cs0, lane, b, false) + at_stage_field(c, sV, trV, ls0, AT_TL, cs0, lane, b, false);
+    if (tid < 32) {
+        const unsigned b = rq_s32(bar);
+        unsigned bytes = at_stage_field(c, sU, trU, T.ls0, AT_TL, T.cs0, lane, b, false) + at_stage_field(c, sV, trV, T.ls0, AT_TL, T.cs0, lane, b, false);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // the buffer was read through the generic proxy
-        if (lane == 0) rq_mbar_expect_tx(bars + buf, bytes);                   // the one arrival of the phase, with the bytes of all lanes
+        if (lane == 0) rq_mbar_expect_tx(bar, bytes);      // the one arrival of the phase, with the bytes of all lanes
         __syncwarp();
-        at_stage_field(c, sU, trU, ls0, AT_TL, cs0, lane, b, true);
-        at_stage_field(c, sV, trV, ls0, AT_TL, cs0, lane, b, true);
-    };
-    if (tid < 32 && (int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
-    int it = 0;
-    for (int n = blockIdx.x; n < ntiles; n += gridDim.x, it++) {
-        const int buf = it & 1;
-        __syncthreads();                                      // everyone is done with the other buffer (tile it - 1)
-        if (tid < 32 && n + (int)gridDim.x < ntiles) stage(n + gridDim.x, buf ^ 1);
-        const int ty = ty0 + n / ntx, tx = n % ntx;
-        const int i0 = max(ty * AT_TI, ib), i1 = min((ty + 1) * AT_TI, ie);
-        ATile T;
-        T.ls0 = ty * AT_TI - (AT_R + 1); T.cs0 = tx * AT_TJ - AT_CH;
-        at_tile_geometry(c, T, AT_TL);
-        // interior tile: everything staged lies in [2, NumX-3] x [2, NumY-3] (and is resident) -> the coordinate clamps
-        // cannot trigger for in-region taps; all cells active: flag of k_tile_flags
-        const bool fast = T.ls0 >= 2 && T.ls0 + AT_TL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
-                          T.ls0 >= c.i_alloc0 && T.ls0 + AT_TL <= c.i_alloc0 + c.lines_alloc && tile_flags[ty * ntx + tx] != 0;
-        const float *sU = reinterpret_cast<const float *>(at_smem + buf * AT_BUF), *sV = sU + AT_TL * AT_PW;
-        at_wait_tiles(bars + buf, (unsigned)(it >> 1) & 1u, bad);
-        const int j = tx * AT_TJ + (tid & 127);
-        if (fast) at_velocity_cells<true, CHECK>(c, T, sU, sV, trU, trV, mask, shU, shV, dstU, dstV, dt, ty * AT_TI, i0, i1, j, bad);
-        else at_velocity_cells<false, CHECK>(c, T, sU, sV, trU, trV, mask, shU, shV, dstU, dstV, dt, ty * AT_TI, i0, i1, j, bad);
+        at_stage_field(c, sU, trU, T.ls0, AT_TL, T.cs0, lane, b, true);
+        at_stage_field(c, sV, trV, T.ls0, AT_TL, T.cs0, lane, b, true);
     }
+    // interior tile: everything staged lies in [2, NumX-3] x [2, NumY-3] (and is resident) -> the coordinate clamps
+    // cannot trigger for in-region taps; all cells active: flag of k_tile_flags
+    const bool fast = T.ls0 >= 2 && T.ls0 + AT_TL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
+                      T.ls0 >= c.i_alloc0 && T.ls0 + AT_TL <= c.i_alloc0 + c.lines_alloc && tile_flags[ty * ntx + tx] != 0;
+    at_wait_tiles(bar, 0, bad);
+    const int j = tx * AT_TJ + (tid & 127);
+    if (fast) at_velocity_cells<true, CHECK>(c, T, sU, sV, trU, trV, mask, shU, shV, dstU, dstV, dt, ty * AT_TI, i0, i1, j, bad);
+    else at_velocity_cells<false, CHECK>(c, T, sU, sV, trU, trV, mask, shU, shV, dstU, dstV, dt, ty * AT_TI, i0, i1, j, bad);
 }
 
 // ---- BFECC velocity: back-trace (+dt, sampling the forward result), error compensation and clamp to the 3x3
@@ -336,57 +330,45 @@ __device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, 
 }
 
 template <bool CHECK>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, AT_MINB)
 k_bfecc_velocity_tile(const AdvCtx c, const float *__restrict__ U, const float *__restrict__ V,
                       const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
                       const float *__restrict__ fwdU, const float *__restrict__ fwdV, float *__restrict__ corrU,
                       float *__restrict__ corrV, const float dt, const int ib, const int ie, int *bad)
 {
     extern __shared__ __align__(128) unsigned char at_smem[];
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(at_smem + 2 * AT_BBUF);
+    float *sFU = reinterpret_cast<float *>(at_smem), *sFV = sFU + AT_BTL * AT_PW;
+    float *sU = sFV + AT_BTL * AT_PW, *sV = sU + AT_BVL * AT_PW;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(at_smem + AT_BBUF);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int ty0 = ib / AT_BTI, ntiles = ntx * (cdiv_dev(ie, AT_BTI) - ty0);
-    if (tid == 0) { rq_mbar_init(bars, 1); rq_mbar_init(bars + 1, 1); }
+    const int ty = ib / AT_BTI + blockIdx.y, tx = blockIdx.x;
+    const int i0 = max(ty * AT_BTI, ib), i1 = min((ty + 1) * AT_BTI, ie);
+    ATile T;
+    T.ls0 = ty * AT_BTI - (AT_R + 1); T.cs0 = tx * AT_TJ - AT_CH;
+    at_tile_geometry(c, T, AT_BTL);
+    const int vls0 = ty * AT_BTI - 1;
+    if (tid == 0) rq_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    auto stage = [&](const int n, const int buf) {            // warp 0: tile n -> buffer buf
-        float *sFU = reinterpret_cast<float *>(at_smem + buf * AT_BBUF), *sFV = sFU + AT_BTL * AT_PW;
-        float *sU = sFV + AT_BTL * AT_PW, *sV = sU + AT_BVL * AT_PW;
-        const int t0 = (ty0 + n / ntx) * AT_BTI, ls0 = t0 - (AT_R + 1), vls0 = t0 - 1, cs0 = (n % ntx) * AT_TJ - AT_CH;
-        const unsigned b = rq_s32(bars + buf);
-        unsigned bytes = at_stage_field(c, sFU, fwdU, ls0, AT_BTL, cs0, lane, b, false) + at_stage_field(c, sFV, fwdV, ls0, AT_BTL, cs0, lane, b, false) +
-                         at_stage_field(c, sU, U, vls0, AT_BVL, cs0, lane, b, false) + at_stage_field(c, sV, V, vls0, AT_BVL, cs0, lane, b, false);
+    if (tid < 32) {
+        const unsigned b = rq_s32(bar);
+        unsigned bytes = at_stage_field(c, sFU, fwdU, T.ls0, AT_BTL, T.cs0, lane, b, false) + at_stage_field(c, sFV, fwdV, T.ls0, AT_BTL, T.cs0, lane, b, false) +
+                         at_stage_field(c, sU, U, vls0, AT_BVL, T.cs0, lane, b, false) + at_stage_field(c, sV, V, vls0, AT_BVL, T.cs0, lane, b, false);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) rq_mbar_expect_tx(bars + buf, bytes);
+        if (lane == 0) rq_mbar_expect_tx(bar, bytes);
         __syncwarp();
-        at_stage_field(c, sFU, fwdU, ls0, AT_BTL, cs0, lane, b, true);
-        at_stage_field(c, sFV, fwdV, ls0, AT_BTL, cs0, lane, b, true);
-        at_stage_field(c, sU, U, vls0, AT_BVL, cs0, lane, b, true);
-        at_stage_field(c, sV, V, vls0, AT_BVL, cs0, lane, b, true);
-    };
-    if (tid < 32 && (int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
-    int it = 0;
-    for (int n = blockIdx.x; n < ntiles; n += gridDim.x, it++) {
-        const int buf = it & 1;
-        __syncthreads();                                      // everyone is done with the other buffer (tile it - 1)
-        if (tid < 32 && n + (int)gridDim.x < ntiles) stage(n + gridDim.x, buf ^ 1);
-        const int ty = ty0 + n / ntx, tx = n % ntx;
-        const int i0 = max(ty * AT_BTI, ib), i1 = min((ty + 1) * AT_BTI, ie);
-        ATile T;
-        T.ls0 = ty * AT_BTI - (AT_R + 1); T.cs0 = tx * AT_TJ - AT_CH;
-        at_tile_geometry(c, T, AT_BTL);
-        const int vls0 = ty * AT_BTI - 1;
-        // the per-tile flag refers to tiles of AT_TI lines: the flag of the AT_TI tile that contains this AT_BTI tile
-        const bool fast = T.ls0 >= 2 && T.ls0 + AT_BTL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
-                          T.ls0 >= c.i_alloc0 && T.ls0 + AT_BTL <= c.i_alloc0 + c.lines_alloc &&
-                          tile_flags[((ty * AT_BTI) / AT_TI) * ntx + tx] != 0;
-        const float *sFU = reinterpret_cast<const float *>(at_smem + buf * AT_BBUF), *sFV = sFU + AT_BTL * AT_PW;
-        const float *sU = sFV + AT_BTL * AT_PW, *sV = sU + AT_BVL * AT_PW;
-        at_wait_tiles(bars + buf, (unsigned)(it >> 1) & 1u, bad);
-        const int j = tx * AT_TJ + (tid & 127);
-        if (fast) at_bfecc_cells<true, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, ty * AT_BTI, i0, i1, j, bad);
-        else at_bfecc_cells<false, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, ty * AT_BTI, i0, i1, j, bad);
+        at_stage_field(c, sFU, fwdU, T.ls0, AT_BTL, T.cs0, lane, b, true);
+        at_stage_field(c, sFV, fwdV, T.ls0, AT_BTL, T.cs0, lane, b, true);
+        at_stage_field(c, sU, U, vls0, AT_BVL, T.cs0, lane, b, true);
+        at_stage_field(c, sV, V, vls0, AT_BVL, T.cs0, lane, b, true);
     }
+    // the per-tile flag refers to tiles of AT_TI lines: the flag of the AT_TI tile that contains this AT_BTI tile
+    const bool fast = T.ls0 >= 2 && T.ls0 + AT_BTL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
+                      T.ls0 >= c.i_alloc0 && T.ls0 + AT_BTL <= c.i_alloc0 + c.lines_alloc &&
+                      tile_flags[((ty * AT_BTI) / AT_TI) * ntx + tx] != 0;
+    at_wait_tiles(bar, 0, bad);
+    const int j = tx * AT_TJ + (tid & 127);
+    if (fast) at_bfecc_cells<true, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, ty * AT_BTI, i0, i1, j, bad);
+    else at_bfecc_cells<false, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, ty * AT_BTI, i0, i1, j, bad);
 }

@@ -989,8 +989,7 @@ static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
         if (adv_full) { ADV_LAUNCH(k_advect_velocity_full, c, sU, sV, mk, aU, aV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
         ProfScope _ks(h, FB_PROF_K_ADVECT_VELOCITY); \
-        const int _nt = h->tile_ntx * (cdiv(ie, AT_TI) - (ib) / AT_TI); \
-        const dim3 _grid(_nt < 2 * h->nsm ? _nt : 2 * h->nsm, 1, 1); \
+        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_TI) - (ib) / AT_TI, 1); \
         if (h->cfg.nranks > 1) k_advect_velocity_tile<true><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         else k_advect_velocity_tile<false><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         CKL("k_advect_velocity_tile"); } while (0)
@@ -998,8 +997,7 @@ static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
         if (adv_full) { ADV_LAUNCH(k_bfecc_velocity_correct, c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
         ProfScope _ks(h, FB_PROF_K_BFECC_VELOCITY); \
-        const int _nt = h->tile_ntx * (cdiv(ie, AT_BTI) - (ib) / AT_BTI); \
-        const dim3 _grid(_nt < 2 * h->nsm ? _nt : 2 * h->nsm, 1, 1); \
+        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_BTI) - (ib) / AT_BTI, 1); \
         if (h->cfg.nranks > 1) k_bfecc_velocity_tile<true><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
         else k_bfecc_velocity_tile<false><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
         CKL("k_bfecc_velocity_tile"); } while (0)
@@ -1064,7 +1062,9 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         }
     }
     const bool pressure_form = p->solver == FB_SOLVER_REDBLACK_PRESSURE;
-    static const bool rbq_ring = getenv("FLUIDB200_RBQ_RING") != nullptr;       // A/B: the shared-memory ring pipeline of round 1
+    // k_rbq_fused (shared-memory ring, 24 warps per SM) is the default: the register pipelines of rbq_stream.cuh measured slower
+    // at 4098^2 (0.25 - 0.32 ms against 0.18); FLUIDB200_RBQ_STREAM=1 selects them (A/B, profiles/r02_rbq_stream.md)
+    static const bool rbq_ring = getenv("FLUIDB200_RBQ_STREAM") == nullptr;
     if (pressure_form && !rbq_ring) {
         // k_rbq_stream: one warp (= CTA) per strip x chunk; all warps resident in ONE wave, least halo recomputation
         const int lines = ie - ib;

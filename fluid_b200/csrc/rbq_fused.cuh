@@ -253,13 +253,20 @@ __device__ __forceinline__ float4 rq_update(const float4 qo, const float4 up, co
                                             const float4 nd, const unsigned code, const float2 nwd2, const float2 c44,
                                             const float *__restrict__ tw, float4 &t_out)
 {
-    // left / right neighbours of cell k: other-parity indices q0+k-1+A and q0+k+A
-    float2 l01, l23, r01, r23;
-    if (A) { l01 = make_float2(ot.x, ot.y); l23 = make_float2(ot.z, ot.w); r01 = make_float2(ot.y, ot.z); r23 = make_float2(ot.w, ox); }
-    else   { l01 = make_float2(ox, ot.x);   l23 = make_float2(ot.y, ot.z); r01 = make_float2(ot.x, ot.y); r23 = make_float2(ot.z, ot.w); }
-    // nb = ((q[i-1,j] + q[i+1,j]) + q[i,j-1]) + q[i,j+1];  t = nb - D0
-    const float2 nb01 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.x, dn.y), make_float2(up.x, up.y)), l01), r01);
-    const float2 nb23 = __fadd2_rn(__fadd2_rn(__fadd2_rn(make_float2(dn.z, dn.w), make_float2(up.z, up.w)), l23), r23);
+    // nb = ((q[i-1,j] + q[i+1,j]) + q[i,j-1]) + q[i,j+1];  t = nb - D0.  The neighbour vector that is shifted by one cell
+    // against the register pairs (left for even columns, right for odd ones) is added with scalar FADDs: assembling the
+    // misaligned pairs a packed add needs cost two moves per pair (~25 moves per sweep step, ncu round 1)
+    float2 nb01 = __fadd2_rn(make_float2(dn.x, dn.y), make_float2(up.x, up.y));
+    float2 nb23 = __fadd2_rn(make_float2(dn.z, dn.w), make_float2(up.z, up.w));
+    if (A) {               // odd columns: left = (o0, o1, o2, o3), right = (o1, o2, o3, ox)
+        nb01 = __fadd2_rn(nb01, make_float2(ot.x, ot.y));
+        nb23 = __fadd2_rn(nb23, make_float2(ot.z, ot.w));
+        nb01.x = nb01.x + ot.y; nb01.y = nb01.y + ot.z; nb23.x = nb23.x + ot.w; nb23.y = nb23.y + ox;
+    } else {               // even columns: left = (ox, o0, o1, o2), right = (o0, o1, o2, o3)
+        nb01.x = nb01.x + ox; nb01.y = nb01.y + ot.x; nb23.x = nb23.x + ot.y; nb23.y = nb23.y + ot.z;
+        nb01 = __fadd2_rn(nb01, make_float2(ot.x, ot.y));
+        nb23 = __fadd2_rn(nb23, make_float2(ot.z, ot.w));
+    }
     const float2 t01 = __fadd2_rn(nb01, make_float2(nd.x, nd.y));
     const float2 t23 = __fadd2_rn(nb23, make_float2(nd.z, nd.w));
     // q' = fma(wd*rs, t, fma(-wd, q, q))
