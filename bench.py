@@ -375,7 +375,7 @@ def run_projection(args, rank, world, local):
     proj_ms = allmax(phases["project"][0] / max(phases["project"][1], 1))
     cells_rank = (f.i_hi - f.i_lo) * NY
     achieved = 24 * cells_rank / (proj_ms * 1e-3) / 1e9
-    kname = "k_rbq_stream" if args.solver == "pressure" else "k_rb_fused"
+    kname = ("k_rbq_stream" if os.environ.get("FLUIDB200_RBQ_STREAM") else "k_rbq_fused") if args.solver == "pressure" else "k_rb_fused"
     traffic, traffic_src = traffic_for(args.workload, kname)
     roofline = {"bound": "hbm", "kernel": kname, "phase": "project",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -639,7 +639,10 @@ def run_preset(args, workload, rank, world, local, primary):
     cells_rank = cells_total // world
     kernel_alg_bytes = {"k_pressure_solve": 24, "k_advect_velocity_full": 20, "k_bfecc_velocity_correct": 28,
                         "k_advect_smoke_full": 20, "k_bfecc_smoke_correct": 24, "k_confine_turbulence": 20}
-    kernel_real = {"k_pressure_solve": {"pressure": "k_rbq_stream", "redblack": "k_rb_fused", "exact": "k_gs_wavefront"}[args.solver]}
+    kernel_real = {"k_pressure_solve": {"pressure": "k_rbq_stream" if os.environ.get("FLUIDB200_RBQ_STREAM") else "k_rbq_fused",
+                                        "redblack": "k_rb_fused", "exact": "k_gs_wavefront"}[args.solver],
+                   "k_advect_velocity_full": "k_advect_velocity_full" if os.environ.get("FLUIDB200_ADV_FULL") else "k_advect_velocity_tile",
+                   "k_bfecc_velocity_correct": "k_bfecc_velocity_correct" if os.environ.get("FLUIDB200_ADV_FULL") else "k_bfecc_velocity_tile"}
     kern = {}
     for k in L.PROF_KERNELS:
         tot, calls = phases.get(k, (0.0, 0))
@@ -680,7 +683,7 @@ def run_preset(args, workload, rank, world, local, primary):
         "config": {"workload": workload, "restates": cfg_desc, "grid_per_gpu": [width + 2, height + 2],
                    "grid_total": [width * world + 2, height + 2], "cells_total": cells_total, "preset": pname, "bfecc": bfecc,
                    "confinement": conf, "turbulence": 0.02, "dt": preset.dt, "parallelism": parallelism,
-                   "solver": {"pressure": "red-black SOR in pressure form, 8 iterations fused in one pass (k_rbq_stream), "
+                   "solver": {"pressure": "red-black SOR in pressure form, 8 iterations fused in one pass (k_rbq_fused), "
                                           "reference omega schedule with damped close (1.0, 0.5)",
                               "redblack": "red-black SOR on the face velocities, 8 iterations fused, "
                                           "reference omega schedule with damped close (1.0, 0.5)",

@@ -122,6 +122,33 @@ __device__ __forceinline__ float sample_tile(const AdvCtx &c, const ATile &T, co
     return sample_far<FLD, CHECK>(c, gdata, x, y, bad);
 }
 
+// The same sample split in two for the straight-line bodies: at_tap() computes the interpolation from the staged tile
+// UNCONDITIONALLY (a tap pair outside the staged region reads element 0 instead and its value is discarded) and says
+// whether the pair was inside; the caller re-samples the outsiders through sample_far afterwards.  Several samples then
+// sit in ONE basic block and their dependent chains interleave (with the branch inside every sample a warp issued one
+// instruction every ~10 cycles, ncu round 2).  Interior tiles only (no coordinate clamps).
+template <int FLD>
+__device__ __forceinline__ float at_tap(const AdvCtx &c, const ATile &T, const float *__restrict__ sm, const float x, const float y, bool &inside)
+{
+    const float xs = (FLD == 0) ? x : x - c.h2;
+    const float ys = (FLD == 1) ? y : y - c.h2;
+    const float2 s2 = make_float2(xs, ys), h1 = make_float2(c.h1, c.h1);
+    const float2 q = __fmul2_rn(s2, h1);
+    const int x0 = __float2int_rd(q.x), y0 = __float2int_rd(q.y);
+    inside = (unsigned)(x0 - T.vl0) < T.nl && (unsigned)(y0 - T.vc0) < T.nc;
+    const float fx = (float)x0, fy = (float)y0;
+    const float2 f0h = __fmul2_rn(make_float2(fx, fy), make_float2(c.h, c.h));
+    const float2 t = __fmul2_rn(__fadd2_rn(s2, make_float2(-f0h.x, -f0h.y)), h1);
+    const float2 sxy = __fadd2_rn(make_float2(1.0f, 1.0f), make_float2(-t.x, -t.y));
+    const int off = inside ? (x0 - T.ls0) * AT_PW + (y0 - T.cs0) : 0;
+    const float *p = sm + off;
+    const float f00 = p[0], f10 = p[AT_PW], f11 = p[AT_PW + 1], f01 = p[1];
+    const float w00 = sxy.x * sxy.y, w10 = t.x * sxy.y, w11 = t.x * t.y, w01 = sxy.x * t.y;
+    const float2 pA = __fmul2_rn(make_float2(w00, w10), make_float2(f00, f10));
+    const float2 pB = __fmul2_rn(make_float2(w01, w11), make_float2(f01, f11));
+    return ((pA.x + pA.y) + pB.y) + pB.x;
+}
+
 // Stage lines [ls0, ls0 + nlines) x columns [cs0, cs0 + AT_PW) of `src` (clipped to the lines this rank holds and to the
 // pitch) into `dst`; called by warp 0, one line per lane and round.  `issue` false: only count the bytes this lane will ask for.
 __device__ __forceinline__ unsigned at_stage_field(const AdvCtx &c, float *dst, const float *__restrict__ src, const int ls0, const int nlines,
@@ -182,41 +209,67 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
     size_t o = (size_t)(ia - c.i_alloc0) * c.pitch + j;
     float um = pu[-1], u = pu[0];                  // U[i, j-1], U[i, j]
     float vm0 = pv[-AT_PW], vm1 = pv[-AT_PW + 1];  // V[i-1, j], V[i-1, j+1]
+    if (FAST) {
+        // straight-line body, two lines (four samples) per trip: every face is traced, nothing is selected
+        const size_t P = (size_t)c.pitch;
+        int i = ia;
+        for (; i + 1 < ib; i += 2, pu += 2 * AT_PW, pv += 2 * AT_PW, o += 2 * P) {
+            const float upm = pu[AT_PW - 1], up = pu[AT_PW], upm2 = pu[2 * AT_PW - 1], up2 = pu[2 * AT_PW];
+            const float v = pv[0], vn = pv[1], v2 = pv[AT_PW], vn2 = pv[AT_PW + 1];
+            const float xi = (float)i * c.h, xi2 = (float)(i + 1) * c.h;
+            const float av = (((vm0 + v) + vm1) + vn) * 0.25f, au = (((um + u) + upm) + up) * 0.25f;
+            const float av2 = (((v + v2) + vn) + vn2) * 0.25f, au2 = (((upm + up) + upm2) + up2) * 0.25f;
+            const float xa = xi - dt * u, ya = yj2 - dt * av, xb = (xi + c.h2) - dt * au, yb = yj - dt * v;
+            const float xc = xi2 - dt * up, yc = yj2 - dt * av2, xd = (xi2 + c.h2) - dt * au2, yd = yj - dt * v2;
+            bool ina, inb, inc, ind;
+            float oa = at_tap<0>(c, T, sU, xa, ya, ina), ob = at_tap<1>(c, T, sV, xb, yb, inb);
+            float oc = at_tap<0>(c, T, sU, xc, yc, inc), od = at_tap<1>(c, T, sV, xd, yd, ind);
+            if (!(ina && inb && inc && ind)) {          // a trace left the staged region: the global sampler, same result
+                if (!ina) oa = sample_far<0, CHECK>(c, trU, xa, ya, bad);
+                if (!inb) ob = sample_far<1, CHECK>(c, trV, xb, yb, bad);
+                if (!inc) oc = sample_far<0, CHECK>(c, trU, xc, yc, bad);
+                if (!ind) od = sample_far<1, CHECK>(c, trV, xd, yd, bad);
+            }
+            dstU[o] = oa; dstV[o] = ob; dstU[o + P] = oc; dstV[o + P] = od;
+            um = upm2; u = up2; vm0 = v2; vm1 = vn2;
+        }
+        if (i < ib) {
+            const float upm = pu[AT_PW - 1], up = pu[AT_PW];
+            const float v = pv[0], vn = pv[1];
+            const float xi = (float)i * c.h;
+            const float av = (((vm0 + v) + vm1) + vn) * 0.25f, au = (((um + u) + upm) + up) * 0.25f;
+            const float du = dt * u, dv = dt * av, du2 = dt * au, dv2 = dt * v;
+            dstU[o] = sample_tile<0, true, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
+            dstV[o] = sample_tile<1, true, CHECK>(c, T, sV, trV, (xi + c.h2) - du2, yj - dv2, bad);
+        }
+        return;
+    }
 #pragma unroll 2
     for (int i = ia; i < ib; i++, pu += AT_PW, pv += AT_PW, o += c.pitch) {
         const float upm = pu[AT_PW - 1], up = pu[AT_PW];      // U[i+1, j-1], U[i+1, j]
         const float v = pv[0], vn = pv[1];                    // V[i, j], V[i, j+1]
         const float xi = (float)i * c.h;
         float outU, outV;
-        if (FAST) {
-            const float av = (((vm0 + v) + vm1) + vn) * 0.25f;        // avgV (fluid.go:342-347)
-            const float au = (((um + u) + upm) + up) * 0.25f;         // avgU (fluid.go:335-340)
+        const unsigned m = mask[o];
+        const bool in_loop = i >= 1 && j >= 1;                       // loops start at 1 (fluid.go:300-301); j < NumY holds
+        const bool act_u = in_loop && (m & MK_C) && (m & MK_XM) && j < c.NY - 1;
+        const bool act_v = in_loop && (m & MK_C) && (m & MK_YM) && i < c.NX - 1;
+        const bool ring = i == 0 || j == 0 || i == c.NX - 1 || j == c.NY - 1;
+        if (act_u) {
+            // avgV (fluid.go:342-347): V[i-1,j] + V[i,j] + V[i-1,j+1] + V[i,j+1]
+            const float av = (((vm0 + v) + vm1) + vn) * 0.25f;
             const float du = dt * u, dv = dt * av;
-            outU = sample_tile<0, true, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
-            const float du2 = dt * au, dv2 = dt * v;
-            outV = sample_tile<1, true, CHECK>(c, T, sV, trV, (xi + c.h2) - du2, yj - dv2, bad);
+            outU = sample_tile<0, false, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
         } else {
-            const unsigned m = mask[o];
-            const bool in_loop = i >= 1 && j >= 1;                       // loops start at 1 (fluid.go:300-301); j < NumY holds
-            const bool act_u = in_loop && (m & MK_C) && (m & MK_XM) && j < c.NY - 1;
-            const bool act_v = in_loop && (m & MK_C) && (m & MK_YM) && i < c.NX - 1;
-            const bool ring = i == 0 || j == 0 || i == c.NX - 1 || j == c.NY - 1;
-            if (act_u) {
-                // avgV (fluid.go:342-347): V[i-1,j] + V[i,j] + V[i-1,j+1] + V[i,j+1]
-                const float av = (((vm0 + v) + vm1) + vn) * 0.25f;
-                const float du = dt * u, dv = dt * av;
-                outU = sample_tile<0, false, CHECK>(c, T, sU, trU, xi - du, yj2 - dv, bad);
-            } else {
-                outU = ring ? u : shU[o];
-            }
-            if (act_v) {
-                // avgU (fluid.go:335-340): U[i,j-1] + U[i,j] + U[i+1,j-1] + U[i+1,j]
-                const float au = (((um + u) + upm) + up) * 0.25f;
-                const float du = dt * au, dv = dt * v;
-                outV = sample_tile<1, false, CHECK>(c, T, sV, trV, (xi + c.h2) - du, yj - dv, bad);
-            } else {
-                outV = ring ? v : shV[o];
-            }
+            outU = ring ? u : shU[o];
+        }
+        if (act_v) {
+            // avgU (fluid.go:335-340): U[i,j-1] + U[i,j] + U[i+1,j-1] + U[i+1,j]
+            const float au = (((um + u) + upm) + up) * 0.25f;
+            const float du = dt * au, dv = dt * v;
+            outV = sample_tile<1, false, CHECK>(c, T, sV, trV, (xi + c.h2) - du, yj - dv, bad);
+        } else {
+            outV = ring ? v : shV[o];
         }
         dstU[o] = outU;
         dstV[o] = outV;
@@ -296,17 +349,30 @@ __device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, 
         if (FAST || (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2)) {
             const float xi = (float)i * c.h;
             float bwdU = 0.0f, bwdV = 0.0f;                       // bwd arrays start as zeros (fluid.go:938-939)
-            unsigned m = MK_C | MK_XM | MK_YM;
-            if (!FAST) m = mask[o];
-            if ((m & MK_C) && (m & MK_XM)) {
+            if (FAST) {
+                // every face is traced; both samples unconditionally from the tile, outsiders re-sampled afterwards
                 const float av = (((va[1] + v) + va[2]) + vb[2]) * 0.25f;          // V[i-1,j] + V[i,j] + V[i-1,j+1] + V[i,j+1]
-                const float du = dt * u, dv = dt * av;
-                bwdU = sample_tile<0, FAST, CHECK>(c, T, sFU, fwdU, xi + du, yj2 + dv, bad);
-            }
-            if ((m & MK_C) && (m & MK_YM)) {
                 const float au = (((ub[0] + u) + uc[0]) + uc[1]) * 0.25f;          // U[i,j-1] + U[i,j] + U[i+1,j-1] + U[i+1,j]
-                const float du = dt * au, dv = dt * v;
-                bwdV = sample_tile<1, FAST, CHECK>(c, T, sFV, fwdV, (xi + c.h2) + du, yj + dv, bad);
+                const float xa = xi + dt * u, ya = yj2 + dt * av, xb = (xi + c.h2) + dt * au, yb = yj + dt * v;
+                bool ina, inb;
+                bwdU = at_tap<0>(c, T, sFU, xa, ya, ina);
+                bwdV = at_tap<1>(c, T, sFV, xb, yb, inb);
+                if (!(ina && inb)) {
+                    if (!ina) bwdU = sample_far<0, CHECK>(c, fwdU, xa, ya, bad);
+                    if (!inb) bwdV = sample_far<1, CHECK>(c, fwdV, xb, yb, bad);
+                }
+            } else {
+                const unsigned m = mask[o];
+                if ((m & MK_C) && (m & MK_XM)) {
+                    const float av = (((va[1] + v) + va[2]) + vb[2]) * 0.25f;
+                    const float du = dt * u, dv = dt * av;
+                    bwdU = sample_tile<0, false, CHECK>(c, T, sFU, fwdU, xi + du, yj2 + dv, bad);
+                }
+                if ((m & MK_C) && (m & MK_YM)) {
+                    const float au = (((ub[0] + u) + uc[0]) + uc[1]) * 0.25f;
+                    const float du = dt * au, dv = dt * v;
+                    bwdV = sample_tile<1, false, CHECK>(c, T, sFV, fwdV, (xi + c.h2) + du, yj + dv, bad);
+                }
             }
             // clampToNeighbors (fluid.go:1094-1120): min / max over the 3x3 neighbourhood of the original field
             float loU = fminf(fminf(ua[0], ua[1]), ua[2]), hiU = fmaxf(fmaxf(ua[0], ua[1]), ua[2]);

@@ -169,7 +169,7 @@ __device__ __forceinline__ void rq_arrive_a(unsigned bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 #ifndef RQ_TRYWAIT_HINT
-#define RQ_TRYWAIT_HINT 0x4000      // ns a waiting warp may sleep per poll (0: no hint, the hardware default)
+#define RQ_TRYWAIT_HINT 0           // ns a waiting warp may sleep per poll (0: no hint, the hardware default: measured best, 0.172 against 0.177 ms)
 #endif
 __device__ __forceinline__ bool rq_mbar_try_a(unsigned bar, unsigned parity)
 {
