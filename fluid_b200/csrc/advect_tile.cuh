@@ -6,8 +6,10 @@
 // access: 4 L1 wavefronts per tap instruction (ncu round 1: LSU data pipe 83 %, issue slots 81 %, ~180 / ~260
 // instructions per cell, 0.50 / 0.47 of the HBM peak).  Here a CTA owns the tile of AT_TI lines x AT_TJ columns with the
 // GLOBAL index (ty, tx) -- tile origins are multiples of (AT_TI, AT_TJ) whatever line range a launch covers:
-//   * the sampled planes plus a halo of AT_R + 1 lines / 8 columns are staged in shared memory by TMA (one
-//     cp.async.bulk per line and field, completion counted on one mbarrier);
+//   * the sampled planes plus a halo of AT_R + 1 lines / 8 columns are staged in shared memory by TMA: ONE 2-D tensor-map
+//     copy per plane (cp.async.bulk.tensor.2d, out-of-bounds elements zero-filled, completion counted on one mbarrier).
+//     The first form of these kernels issued one 1-D bulk copy per line and plane (92 - 156 copies of 576 B per tile) and
+//     40 - 50 % of its stall samples were warps waiting for the tile (ncu, round 2);
 //   * ONE LANE PER CELL along j: the four taps of a warp are unit-stride LDS (one wavefront each), at 32-bit shared
 //     addresses with immediate offsets (+1, +pitch, +pitch+1);
 //   * a tap pair that lies inside the staged region needs neither the `min(x0+1, NumX-1)` collapse nor the
@@ -25,8 +27,9 @@
 //     sampler sample_fast<> on the ORIGINAL coordinates, out of line: same result, slower, rare.
 // The arithmetic per face is the reference's, operation for operation (same code as sample_fast).
 #pragma once
+#include <cuda.h>             // CUtensorMap
 #include "advect_fused.cuh"
-#include "rbq_fused.cuh"      // mbarrier / TMA helpers
+#include "rbq_fused.cuh"      // mbarrier helpers
 
 #ifndef AT_TI
 #define AT_TI 32              // lines per tile
@@ -149,22 +152,12 @@ __device__ __forceinline__ float at_tap(const AdvCtx &c, const ATile &T, const f
     return ((pA.x + pA.y) + pB.y) + pB.x;
 }
 
-// Stage lines [ls0, ls0 + nlines) x columns [cs0, cs0 + AT_PW) of `src` (clipped to the lines this rank holds and to the
-// pitch) into `dst`; called by warp 0, one line per lane and round.  `issue` false: only count the bytes this lane will ask for.
-__device__ __forceinline__ unsigned at_stage_field(const AdvCtx &c, float *dst, const float *__restrict__ src, const int ls0, const int nlines,
-                                                   const int cs0, const int lane, const unsigned bar, const bool issue)
+// One 2-D tensor-map copy: the box of the map (AT_PW columns x its line count) whose first element is (line ls0, column cs0)
+// of the plane -> dst; coordinates are relative to the plane's first allocated line and may lie outside it (zero fill).
+__device__ __forceinline__ void at_tensor_load(float *dst, const CUtensorMap *tm, const int col, const int line, const unsigned bar)
 {
-    const int la = max(ls0, max(c.i_alloc0, 0)), lb = min(ls0 + nlines, min(c.i_alloc0 + c.lines_alloc, c.NX));
-    const int ca = max(cs0, 0), cb = min(cs0 + AT_PW, c.pitch);
-    if (cb <= ca) return 0;
-    const unsigned bytes = (unsigned)(cb - ca) * 4u;
-    unsigned total = 0;
-#pragma unroll 1
-    for (int l = la + lane; l < lb; l += 32) {
-        if (issue) rq_tma_load(rq_s32(dst + (l - ls0) * AT_PW + (ca - cs0)), src + (size_t)(l - c.i_alloc0) * c.pitch + ca, bytes, bar);
-        total += bytes;
-    }
-    return total;
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(rq_s32(dst)), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(col), "r"(line), "r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void at_tile_geometry(const AdvCtx &c, ATile &T, const int nlines)
@@ -282,7 +275,8 @@ __device__ __forceinline__ void at_velocity_cells(const AdvCtx &c, const ATile &
 // the one that holds line ib.
 template <bool CHECK>
 __global__ void __launch_bounds__(AT_THREADS, AT_MINB)
-k_advect_velocity_tile(const AdvCtx c, const float *__restrict__ trU, const float *__restrict__ trV,
+k_advect_velocity_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
+                       const float *__restrict__ trU, const float *__restrict__ trV,
                        const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
                        const float *__restrict__ shU, const float *__restrict__ shV, float *__restrict__ dstU,
                        float *__restrict__ dstV, const float dt, const int ib, const int ie, int *bad)
@@ -290,7 +284,7 @@ k_advect_velocity_tile(const AdvCtx c, const float *__restrict__ trU, const floa
     extern __shared__ __align__(128) unsigned char at_smem[];
     float *sU = reinterpret_cast<float *>(at_smem), *sV = sU + AT_TL * AT_PW;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(at_smem + AT_BUF);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int ty = ib / AT_TI + blockIdx.y, tx = blockIdx.x;
     const int i0 = max(ty * AT_TI, ib), i1 = min((ty + 1) * AT_TI, ie);
     ATile T;
@@ -299,15 +293,11 @@ k_advect_velocity_tile(const AdvCtx c, const float *__restrict__ trU, const floa
     if (tid == 0) rq_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    if (tid < 32) {
+    if (tid == 0) {
         const unsigned b = rq_s32(bar);
-        unsigned bytes = at_stage_field(c, sU, trU, T.ls0, AT_TL, T.cs0, lane, b, false) + at_stage_field(c, sV, trV, T.ls0, AT_TL, T.cs0, lane, b, false);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-        if (lane == 0) rq_mbar_expect_tx(bar, bytes);      // the one arrival of the phase, with the bytes of all lanes
-        __syncwarp();
-        at_stage_field(c, sU, trU, T.ls0, AT_TL, T.cs0, lane, b, true);
-        at_stage_field(c, sV, trV, T.ls0, AT_TL, T.cs0, lane, b, true);
+        rq_mbar_expect_tx(bar, 2u * AT_TL * AT_PW * 4u);          // the whole boxes count, zero-filled parts included
+        at_tensor_load(sU, &tmU, T.cs0, T.ls0 - c.i_alloc0, b);
+        at_tensor_load(sV, &tmV, T.cs0, T.ls0 - c.i_alloc0, b);
     }
     // interior tile: everything staged lies in [2, NumX-3] x [2, NumY-3] (and is resident) -> the coordinate clamps
     // cannot trigger for in-region taps; all cells active: flag of k_tile_flags
@@ -397,7 +387,9 @@ __device__ __forceinline__ void at_bfecc_cells(const AdvCtx &c, const ATile &T, 
 
 template <bool CHECK>
 __global__ void __launch_bounds__(AT_THREADS, AT_MINB)
-k_bfecc_velocity_tile(const AdvCtx c, const float *__restrict__ U, const float *__restrict__ V,
+k_bfecc_velocity_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ CUtensorMap tmFU, const __grid_constant__ CUtensorMap tmFV,
+                      const float *__restrict__ U, const float *__restrict__ V,
                       const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
                       const float *__restrict__ fwdU, const float *__restrict__ fwdV, float *__restrict__ corrU,
                       float *__restrict__ corrV, const float dt, const int ib, const int ie, int *bad)
@@ -406,7 +398,7 @@ k_bfecc_velocity_tile(const AdvCtx c, const float *__restrict__ U, const float *
     float *sFU = reinterpret_cast<float *>(at_smem), *sFV = sFU + AT_BTL * AT_PW;
     float *sU = sFV + AT_BTL * AT_PW, *sV = sU + AT_BVL * AT_PW;
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(at_smem + AT_BBUF);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int ty = ib / AT_BTI + blockIdx.y, tx = blockIdx.x;
     const int i0 = max(ty * AT_BTI, ib), i1 = min((ty + 1) * AT_BTI, ie);
     ATile T;
@@ -416,18 +408,13 @@ k_bfecc_velocity_tile(const AdvCtx c, const float *__restrict__ U, const float *
     if (tid == 0) rq_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    if (tid < 32) {
+    if (tid == 0) {
         const unsigned b = rq_s32(bar);
-        unsigned bytes = at_stage_field(c, sFU, fwdU, T.ls0, AT_BTL, T.cs0, lane, b, false) + at_stage_field(c, sFV, fwdV, T.ls0, AT_BTL, T.cs0, lane, b, false) +
-                         at_stage_field(c, sU, U, vls0, AT_BVL, T.cs0, lane, b, false) + at_stage_field(c, sV, V, vls0, AT_BVL, T.cs0, lane, b, false);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-        if (lane == 0) rq_mbar_expect_tx(bar, bytes);
-        __syncwarp();
-        at_stage_field(c, sFU, fwdU, T.ls0, AT_BTL, T.cs0, lane, b, true);
-        at_stage_field(c, sFV, fwdV, T.ls0, AT_BTL, T.cs0, lane, b, true);
-        at_stage_field(c, sU, U, vls0, AT_BVL, T.cs0, lane, b, true);
-        at_stage_field(c, sV, V, vls0, AT_BVL, T.cs0, lane, b, true);
+        rq_mbar_expect_tx(bar, (2u * AT_BTL + 2u * AT_BVL) * AT_PW * 4u);
+        at_tensor_load(sFU, &tmFU, T.cs0, T.ls0 - c.i_alloc0, b);
+        at_tensor_load(sFV, &tmFV, T.cs0, T.ls0 - c.i_alloc0, b);
+        at_tensor_load(sU, &tmU, T.cs0, vls0 - c.i_alloc0, b);
+        at_tensor_load(sV, &tmV, T.cs0, vls0 - c.i_alloc0, b);
     }
     // the per-tile flag refers to tiles of AT_TI lines: the flag of the AT_TI tile that contains this AT_BTI tile
     const bool fast = T.ls0 >= 2 && T.ls0 + AT_BTL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&

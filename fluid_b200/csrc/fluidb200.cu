@@ -9,8 +9,10 @@
 #include "advect_tile.cuh"
 #include "multigrid.cuh"
 
+#include <cudaTypedefs.h>      // PFN_cuTensorMapEncodeTiled (resolved through the runtime: no -lcuda)
 #include <cmath>
 #include <cstdio>
+#include <map>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -38,6 +40,7 @@ struct fb_handle {
     bool rb_attr_set, rbq_attr_set, adv_tile_attr_set;
     unsigned char *tile_flags;                          // per AT_TI x AT_TJ tile: all cells active (advect_tile.cuh)
     int tile_ntx, tile_nty;
+    std::map<std::pair<const void *, int>, CUtensorMap> tmaps;   // (plane, box lines) -> 2-D tensor map of the tile loads
     bool want_stats;
     bool fuse_turb;               // apply addTurbulence in the fused solve's write-out (else its own pass)
     int nsm;
@@ -974,6 +977,36 @@ static AdvCtx adv_ctx(const fb_handle *h)
 // advectVelocity / the BFECC correct pass on shared-memory tiles (advect_tile.cuh); FLUIDB200_ADV_FULL=1 selects the
 // global-gather kernels of round 1 (A/B).  Arguments: (c, srcU, srcV, mask, inU, inV, outU, outV, dt, ib, ie, bad) as for
 // k_advect_velocity_full / k_bfecc_velocity_correct.
+// 2-D tensor map of a plane for the tile kernels' TMA loads: [lines_alloc][pitch] floats, box = box_lines x AT_PW, elements
+// outside the plane read as zero.  Planes live as long as the handle, so the maps are made once per (plane, box).
+static int tile_tmap(fb_handle *h, const float *plane, int box_lines, CUtensorMap *out)
+{
+    const auto key = std::make_pair((const void *)plane, box_lines);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) { *out = it->second; return FB_OK; }
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(h, FB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }
+    const Grid &g = h->g;
+    const cuuint64_t dims[2] = { (cuuint64_t)g.pitch, (cuuint64_t)g.lines_alloc };
+    const cuuint64_t strides[1] = { (cuuint64_t)g.pitch * sizeof(float) };
+    const cuuint32_t box[2] = { (cuuint32_t)AT_PW, (cuuint32_t)box_lines };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUtensorMap tm;
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    h->tmaps[key] = tm;
+    *out = tm;
+    return FB_OK;
+}
+
 static int adv_tile_attrs(fb_handle *h)
 {
     if (h->adv_tile_attr_set) return FB_OK;
@@ -988,18 +1021,21 @@ static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
 #define ADV_VELOCITY_LAUNCH(c, sU, sV, mk, aU, aV, oU, oV, dt, ib, ie, bad) do { \
         if (adv_full) { ADV_LAUNCH(k_advect_velocity_full, c, sU, sV, mk, aU, aV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
+        CUtensorMap _tU, _tV; TRY(tile_tmap(h, sU, AT_TL, &_tU)); TRY(tile_tmap(h, sV, AT_TL, &_tV)); \
         ProfScope _ks(h, FB_PROF_K_ADVECT_VELOCITY); \
         const dim3 _grid(h->tile_ntx, cdiv(ie, AT_TI) - (ib) / AT_TI, 1); \
-        if (h->cfg.nranks > 1) k_advect_velocity_tile<true><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
-        else k_advect_velocity_tile<false><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
+        if (h->cfg.nranks > 1) k_advect_velocity_tile<true><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, _tU, _tV, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
+        else k_advect_velocity_tile<false><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, _tU, _tV, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         CKL("k_advect_velocity_tile"); } while (0)
 #define ADV_BFECC_VELOCITY_LAUNCH(c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad) do { \
         if (adv_full) { ADV_LAUNCH(k_bfecc_velocity_correct, c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
+        CUtensorMap _tU, _tV, _tFU, _tFV; \
+        TRY(tile_tmap(h, sU, AT_BVL, &_tU)); TRY(tile_tmap(h, sV, AT_BVL, &_tV)); TRY(tile_tmap(h, fU, AT_BTL, &_tFU)); TRY(tile_tmap(h, fV, AT_BTL, &_tFV)); \
         ProfScope _ks(h, FB_PROF_K_BFECC_VELOCITY); \
         const dim3 _grid(h->tile_ntx, cdiv(ie, AT_BTI) - (ib) / AT_BTI, 1); \
-        if (h->cfg.nranks > 1) k_bfecc_velocity_tile<true><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
-        else k_bfecc_velocity_tile<false><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
+        if (h->cfg.nranks > 1) k_bfecc_velocity_tile<true><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, _tU, _tV, _tFU, _tFV, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
+        else k_bfecc_velocity_tile<false><<<_grid, AT_THREADS, AT_BSMEM, h->stream>>>(c, _tU, _tV, _tFU, _tFV, sU, sV, mk, h->tile_flags, h->tile_ntx, fU, fV, oU, oV, dt, ib, ie, bad); \
         CKL("k_bfecc_velocity_tile"); } while (0)
 
 // newX := X as the reference's copy() leaves them, only when the caller asked for it
