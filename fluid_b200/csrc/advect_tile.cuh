@@ -425,3 +425,309 @@ k_bfecc_velocity_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, c
     if (fast) at_bfecc_cells<true, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, ty * AT_BTI, i0, i1, j, bad);
     else at_bfecc_cells<false, CHECK>(c, T, sU, sV, sFU, sFV, vls0, fwdU, fwdV, mask, corrU, corrV, dt, ty * AT_BTI, i0, i1, j, bad);
 }
+
+// ======================= smoke: advectSmoke (fluid.go:400-434) and the BFECC correct pass (fluid.go:1013-1046) ==========
+// Same structure: the sampled plane (M / fwdM) with the full halo, U and V (and origM for the 3x3 clamp) with a one-line
+// halo, all through tensor-map TMA; a lane per cell, consecutive lines per thread, straight-line body on all-fluid tiles.
+#ifndef AT_STI
+#define AT_STI 16
+#endif
+#define AT_STL (AT_STI + 2 * (AT_R + 1))
+#define AT_SVL (AT_STI + 2)
+#define AT_SSMEM ((AT_STL + 2 * AT_SVL) * AT_PW * 4 + 16)
+#define AT_SBSMEM ((AT_STL + 3 * AT_SVL) * AT_PW * 4 + 16)
+static_assert(AT_TI % AT_STI == 0, "a smoke tile lies inside one flag tile");
+
+template <bool FAST, bool CHECK>
+__device__ __forceinline__ void at_smoke_cells(const AdvCtx &c, const ATile &T, const float *__restrict__ sM, const float *__restrict__ sU,
+                                               const float *__restrict__ sV, const int vls0, const float *__restrict__ M,
+                                               const unsigned char *__restrict__ mask, const float *__restrict__ shM,
+                                               float *__restrict__ dst, const float dt, const float sa, const int tl0, const int i0,
+                                               const int i1, const int j, int *bad)
+{
+    if (j >= c.NY) return;
+    const float y0 = (float)j * c.h + c.h2;
+    const int half = AT_STI / AT_LG;
+    const int ia = max(tl0 + (int)(threadIdx.x >> 7) * half, i0), ib = min(tl0 + ((int)(threadIdx.x >> 7) + 1) * half, i1);
+    if (ia >= ib) return;
+    const float *pu = sU + (ia - vls0) * AT_PW + (j - T.cs0), *pv = sV + (ia - vls0) * AT_PW + (j - T.cs0);
+    const float *pm = sM + (ia - T.ls0) * AT_PW + (j - T.cs0);
+    size_t o = (size_t)(ia - c.i_alloc0) * c.pitch + j;
+    const size_t P = (size_t)c.pitch;
+    float u = pu[0];                                   // U[i, j], carried down the lines
+    if (FAST) {
+        int i = ia;
+        for (; i + 1 < ib; i += 2, pu += 2 * AT_PW, pv += 2 * AT_PW, o += 2 * P) {
+            const float up = pu[AT_PW], up2 = pu[2 * AT_PW];
+            const float v = pv[0], vn = pv[1], v2 = pv[AT_PW], vn2 = pv[AT_PW + 1];
+            const float uu = ((u + up) * 0.5f) * sa, vv = ((v + vn) * 0.5f) * sa;
+            const float uu2 = ((up + up2) * 0.5f) * sa, vv2 = ((v2 + vn2) * 0.5f) * sa;
+            const float xa = ((float)i * c.h + c.h2) - dt * uu, ya = y0 - dt * vv;
+            const float xb = ((float)(i + 1) * c.h + c.h2) - dt * uu2, yb = y0 - dt * vv2;
+            bool ina, inb;
+            float a = at_tap<2>(c, T, sM, xa, ya, ina), b = at_tap<2>(c, T, sM, xb, yb, inb);
+            if (!(ina && inb)) {
+                if (!ina) a = sample_far<2, CHECK>(c, M, xa, ya, bad);
+                if (!inb) b = sample_far<2, CHECK>(c, M, xb, yb, bad);
+            }
+            dst[o] = go_maxf(a, 0.0f);
+            dst[o + P] = go_maxf(b, 0.0f);
+            u = up2;
+        }
+        if (i < ib) {
+            const float up = pu[AT_PW], v = pv[0], vn = pv[1];
+            const float uu = ((u + up) * 0.5f) * sa, vv = ((v + vn) * 0.5f) * sa;
+            const float du = dt * uu, dv = dt * vv;
+            dst[o] = go_maxf(sample_tile<2, true, CHECK>(c, T, sM, M, ((float)i * c.h + c.h2) - du, y0 - dv, bad), 0.0f);
+        }
+        return;
+    }
+    for (int i = ia; i < ib; i++, pu += AT_PW, pv += AT_PW, pm += AT_PW, o += P) {
+        const float up = pu[AT_PW];
+        const float mm = pm[0];
+        float out = mm;                                                       // copyBorder(newM, M) on the ring
+        if (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2) {
+            if (!(mask[o] & MK_C)) {
+                out = shM[o];                                                 // solid: the stale scratch value (Q-6)
+            } else {
+                const float uu = ((u + up) * 0.5f) * sa, vv = ((pv[0] + pv[1]) * 0.5f) * sa;
+                const float du = dt * uu, dv = dt * vv;
+                out = go_maxf(sample_tile<2, false, CHECK>(c, T, sM, M, ((float)i * c.h + c.h2) - du, y0 - dv, bad), 0.0f);
+            }
+        }
+        dst[o] = out;
+        u = up;
+    }
+}
+
+// contract of k_advect_smoke_full without the diffusion term (the host keeps that kernel for viscosityDiffusion > 0)
+template <bool CHECK>
+__global__ void __launch_bounds__(AT_THREADS, 4)
+k_advect_smoke_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmM, const float *__restrict__ M, const unsigned char *__restrict__ mask,
+                    const unsigned char *__restrict__ tile_flags, const int ntx, const float *__restrict__ shM, float *__restrict__ dst,
+                    const float dt, const float sa, const int ib, const int ie, int *bad)
+{
+    extern __shared__ __align__(128) unsigned char at_smem[];
+    float *sM = reinterpret_cast<float *>(at_smem), *sU = sM + AT_STL * AT_PW, *sV = sU + AT_SVL * AT_PW;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sV + AT_SVL * AT_PW);
+    const int tid = threadIdx.x;
+    const int ty = ib / AT_STI + blockIdx.y, tx = blockIdx.x;
+    const int i0 = max(ty * AT_STI, ib), i1 = min((ty + 1) * AT_STI, ie);
+    ATile T;
+    T.ls0 = ty * AT_STI - (AT_R + 1); T.cs0 = tx * AT_TJ - AT_CH;
+    at_tile_geometry(c, T, AT_STL);
+    const int vls0 = ty * AT_STI - 1;
+    if (tid == 0) rq_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned b = rq_s32(bar);
+        rq_mbar_expect_tx(bar, (AT_STL + 2u * AT_SVL) * AT_PW * 4u);
+        at_tensor_load(sM, &tmM, T.cs0, T.ls0 - c.i_alloc0, b);
+        at_tensor_load(sU, &tmU, T.cs0, vls0 - c.i_alloc0, b);
+        at_tensor_load(sV, &tmV, T.cs0, vls0 - c.i_alloc0, b);
+    }
+    const bool fast = T.ls0 >= 2 && T.ls0 + AT_STL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
+                      T.ls0 >= c.i_alloc0 && T.ls0 + AT_STL <= c.i_alloc0 + c.lines_alloc &&
+                      tile_flags[((ty * AT_STI) / AT_TI) * ntx + tx] != 0;
+    at_wait_tiles(bar, 0, bad);
+    const int j = tx * AT_TJ + (tid & 127);
+    if (fast) at_smoke_cells<true, CHECK>(c, T, sM, sU, sV, vls0, M, mask, shM, dst, dt, sa, ty * AT_STI, i0, i1, j, bad);
+    else at_smoke_cells<false, CHECK>(c, T, sM, sU, sV, vls0, M, mask, shM, dst, dt, sa, ty * AT_STI, i0, i1, j, bad);
+}
+
+template <bool FAST, bool CHECK>
+__device__ __forceinline__ void at_bfecc_smoke_cells(const AdvCtx &c, const ATile &T, const float *__restrict__ sF, const float *__restrict__ sO,
+                                                     const float *__restrict__ sU, const float *__restrict__ sV, const int vls0,
+                                                     const float *__restrict__ fwdM, const unsigned char *__restrict__ mask,
+                                                     float *__restrict__ corrM, const float dt, const float sa, const int tl0,
+                                                     const int i0, const int i1, const int j, int *bad)
+{
+    if (j >= c.NY) return;
+    const float y0 = (float)j * c.h + c.h2;
+    const int half = AT_STI / AT_LG;
+    const int ia = max(tl0 + (int)(threadIdx.x >> 7) * half, i0), ib = min(tl0 + ((int)(threadIdx.x >> 7) + 1) * half, i1);
+    if (ia >= ib) return;
+    const int off = (ia - vls0) * AT_PW + (j - T.cs0);
+    const float *pu = sU + off, *pv = sV + off, *po = sO + off;
+    size_t o = (size_t)(ia - c.i_alloc0) * c.pitch + j;
+    float u = pu[0];
+    float ma[3] = { po[-AT_PW - 1], po[-AT_PW], po[-AT_PW + 1] }, mb[3] = { po[-1], po[0], po[1] };      // rows i-1, i of origM
+    for (int i = ia; i < ib; i++, pu += AT_PW, pv += AT_PW, po += AT_PW, o += c.pitch) {
+        const float mc[3] = { po[AT_PW - 1], po[AT_PW], po[AT_PW + 1] };                                  // row i+1
+        const float up = pu[AT_PW];
+        const float om = mb[1];
+        float out = om;                                                       // copy(corrM, origM) leaves the ring alone
+        if (FAST || (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2)) {
+            float bwd = 0.0f;                                                 // bwdM starts as zeros (fluid.go:1013)
+            const float uu = ((u + up) * 0.5f) * sa, vv = ((pv[0] + pv[1]) * 0.5f) * sa;
+            const float du = dt * uu, dv = dt * vv;
+            const float x = ((float)i * c.h + c.h2) + du, y = y0 + dv;
+            if (FAST) {
+                bool in;
+                bwd = at_tap<2>(c, T, sF, x, y, in);
+                if (!in) bwd = sample_far<2, CHECK>(c, fwdM, x, y, bad);
+            } else if (mask[o] & MK_C) {
+                bwd = sample_tile<2, false, CHECK>(c, T, sF, fwdM, x, y, bad);
+            }
+            float lo = fminf(fminf(ma[0], ma[1]), ma[2]), hi = fmaxf(fmaxf(ma[0], ma[1]), ma[2]);
+#pragma unroll
+            for (int q = 0; q < 3; q++) { lo = fminf(fminf(lo, mb[q]), mc[q]); hi = fmaxf(fmaxf(hi, mb[q]), mc[q]); }
+            const float e = (bwd - om) * 0.5f;
+            float val = om - e;
+            val = val < lo ? lo : (val > hi ? hi : val);
+            if (val < 0.0f) val = 0.0f;
+            out = val;
+        }
+        corrM[o] = out;
+        u = up;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { ma[q] = mb[q]; mb[q] = mc[q]; }
+    }
+}
+
+// contract of k_bfecc_smoke_correct
+template <bool CHECK>
+__global__ void __launch_bounds__(AT_THREADS, 4)
+k_bfecc_smoke_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmF, const float *__restrict__ fwdM,
+                   const unsigned char *__restrict__ mask, const unsigned char *__restrict__ tile_flags, const int ntx,
+                   float *__restrict__ corrM, const float dt, const float sa, const int ib, const int ie, int *bad)
+{
+    extern __shared__ __align__(128) unsigned char at_smem[];
+    float *sF = reinterpret_cast<float *>(at_smem), *sO = sF + AT_STL * AT_PW, *sU = sO + AT_SVL * AT_PW, *sV = sU + AT_SVL * AT_PW;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sV + AT_SVL * AT_PW);
+    const int tid = threadIdx.x;
+    const int ty = ib / AT_STI + blockIdx.y, tx = blockIdx.x;
+    const int i0 = max(ty * AT_STI, ib), i1 = min((ty + 1) * AT_STI, ie);
+    ATile T;
+    T.ls0 = ty * AT_STI - (AT_R + 1); T.cs0 = tx * AT_TJ - AT_CH;
+    at_tile_geometry(c, T, AT_STL);
+    const int vls0 = ty * AT_STI - 1;
+    if (tid == 0) rq_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned b = rq_s32(bar);
+        rq_mbar_expect_tx(bar, (AT_STL + 3u * AT_SVL) * AT_PW * 4u);
+        at_tensor_load(sF, &tmF, T.cs0, T.ls0 - c.i_alloc0, b);
+        at_tensor_load(sO, &tmO, T.cs0, vls0 - c.i_alloc0, b);
+        at_tensor_load(sU, &tmU, T.cs0, vls0 - c.i_alloc0, b);
+        at_tensor_load(sV, &tmV, T.cs0, vls0 - c.i_alloc0, b);
+    }
+    const bool fast = T.ls0 >= 2 && T.ls0 + AT_STL <= c.NX - 2 && T.cs0 >= 2 && T.cs0 + AT_PW <= c.NY - 2 &&
+                      T.ls0 >= c.i_alloc0 && T.ls0 + AT_STL <= c.i_alloc0 + c.lines_alloc &&
+                      tile_flags[((ty * AT_STI) / AT_TI) * ntx + tx] != 0;
+    at_wait_tiles(bar, 0, bad);
+    const int j = tx * AT_TJ + (tid & 127);
+    if (fast) at_bfecc_smoke_cells<true, CHECK>(c, T, sF, sO, sU, sV, vls0, fwdM, mask, corrM, dt, sa, ty * AT_STI, i0, i1, j, bad);
+    else at_bfecc_smoke_cells<false, CHECK>(c, T, sF, sO, sU, sV, vls0, fwdM, mask, corrM, dt, sa, ty * AT_STI, i0, i1, j, bad);
+}
+
+// ======================= vorticity confinement + turbulence (fluid.go:449-526) on tiles ==================================
+// Contract of k_confine_turbulence.  U and V of the tile plus a two-cell halo arrive by tensor-map TMA; the curl of the
+// tile plus a one-cell halo is computed into shared memory (the reference's `curl` array never touches HBM), a lane per
+// cell, then every cell applies the force and the turbulence.  The round-1 kernel (4 cells per thread, row loads from
+// global memory) issued one instruction per warp every 18 cycles behind its global loads (ncu round 2: long scoreboard
+// the top stall, 0.35 of the HBM peak on a developed flow).
+#ifndef AT_CTI
+#define AT_CTI 16
+#endif
+#define AT_CVL (AT_CTI + 4)                  // staged lines of U, V
+#define AT_CW 132                            // curl tile pitch: columns j0 - 1 .. j0 + 128 (+ padding)
+#define AT_CSMEM (2 * AT_CVL * AT_PW * 4 + (AT_CTI + 2) * AT_CW * 4 + 16)
+
+__device__ __forceinline__ float at_curl(const AdvCtx &c, const float *__restrict__ sU, const float *__restrict__ sV, const int ls0, const int cs0,
+                                         const unsigned char *__restrict__ mask, const int i, const int j, const float h)
+{
+    if (i < 1 || i > c.NX - 2 || j < 1 || j > c.NY - 2) return 0.0f;
+    if (i - 1 < c.i_alloc0 || i + 1 >= c.i_alloc0 + c.lines_alloc) return 0.0f;
+    if (!(mask[(size_t)(i - c.i_alloc0) * c.pitch + j] & MK_C)) return 0.0f;
+    const float *pu = sU + (i - ls0) * AT_PW + (j - cs0), *pv = sV + (i - ls0) * AT_PW + (j - cs0);
+    const float dvdx = div0((pv[AT_PW] - pv[-AT_PW]) * 0.5f, h);
+    const float dudy = div0((pu[1] - pu[-1]) * 0.5f, h);
+    return dvdx - dudy;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 6)
+k_confine_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
+               const unsigned char *__restrict__ mask, const float *__restrict__ nU, const float *__restrict__ nV,
+               float *__restrict__ dstU, float *__restrict__ dstV, const float h, const float dt, const float confinement,
+               const float turbStrength, const int ib, const int ie, int *bad)
+{
+    extern __shared__ __align__(128) unsigned char at_smem[];
+    float *sU = reinterpret_cast<float *>(at_smem), *sV = sU + AT_CVL * AT_PW;
+    float *sC = sV + AT_CVL * AT_PW;                               // [AT_CTI + 2][AT_CW]: lines t0 - 1 .., columns j0 - 1 ..
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sC + (AT_CTI + 2) * AT_CW);
+    const int tid = threadIdx.x;
+    const int ty = ib / AT_CTI + blockIdx.y, tx = blockIdx.x;
+    const int t0 = ty * AT_CTI, j0 = tx * AT_TJ;
+    const int i0 = max(t0, ib), i1 = min(t0 + AT_CTI, ie);
+    const int ls0 = t0 - 2, cs0 = j0 - AT_CH;
+    if (tid == 0) rq_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned b = rq_s32(bar);
+        rq_mbar_expect_tx(bar, 2u * AT_CVL * AT_PW * 4u);
+        at_tensor_load(sU, &tmU, cs0, ls0 - c.i_alloc0, b);
+        at_tensor_load(sV, &tmV, cs0, ls0 - c.i_alloc0, b);
+    }
+    at_wait_tiles(bar, 0, bad);
+    const int cl = tid & 127, grp = tid >> 7;
+    const int j = j0 + cl;
+    if (confinement != 0.0f) {
+        // curl of lines t0 - 1 .. t0 + AT_CTI, columns j0 - 1 .. j0 + 128: a lane per column, the two edge columns on the side
+        constexpr int CL = (AT_CTI + 2 + AT_LG - 1) / AT_LG;       // curl lines per line group
+        for (int li = grp * CL; li < min((grp + 1) * CL, AT_CTI + 2); li++)
+            sC[li * AT_CW + cl + 1] = at_curl(c, sU, sV, ls0, cs0, mask, t0 - 1 + li, j, h);
+        if (tid < 2 * (AT_CTI + 2)) {
+            const int side = tid >= AT_CTI + 2, li = tid - side * (AT_CTI + 2);
+            sC[li * AT_CW + (side ? AT_TJ + 1 : 0)] = at_curl(c, sU, sV, ls0, cs0, mask, t0 - 1 + li, side ? j0 + AT_TJ : j0 - 1, h);
+        }
+        __syncthreads();
+    }
+    if (j >= c.NY) return;
+    constexpr int half = AT_CTI / AT_LG;
+    const int ia = max(t0 + grp * half, i0), ibb = min(t0 + (grp + 1) * half, i1);
+    for (int i = ia; i < ibb; i++) {
+        const size_t o = (size_t)(i - c.i_alloc0) * c.pitch + j;
+        float u = sU[(i - ls0) * AT_PW + (j - cs0)], v = sV[(i - ls0) * AT_PW + (j - cs0)];
+        if (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2 && (mask[o] & MK_C)) {
+            if (confinement != 0.0f) {
+                const float eps = 1e-5f;
+                const float *pc = sC + (i - t0 + 1) * AT_CW + (cl + 1);
+                const float c0 = pc[0];
+                float gx = div0((fabsf(pc[AT_CW]) - fabsf(pc[-AT_CW])) * 0.5f, h);
+                float gy = div0((fabsf(pc[1]) - fabsf(pc[-1])) * 0.5f, h);
+                const float gx2 = gx * gx, gy2 = gy * gy;
+                const float mag = sqrt0(gx2 + gy2) + eps;
+                gx = div0(gx, mag);
+                gy = div0(gy, mag);
+                const float uu = u * u, vv = v * v;
+                const float localVel = sqrt0(uu + vv);
+                const float lv = localVel * 0.1f;
+                const float strength = confinement * (1.0f + lv);
+                const float fu = ((strength * gy) * c0) * dt;
+                const float fv = ((strength * gx) * c0) * dt;
+                u = u + fu;
+                v = v - fv;
+            }
+            if (turbStrength > 0.0f) {
+                const float uu = u * u, vv = v * v;
+                const float localVel = sqrt0(uu + vv);
+                if (localVel > 0.1f) {
+                    const float noiseU = nU[o] * turbStrength;
+                    const float noiseV = nV[o] * turbStrength;
+                    const float factor = fminf(localVel * 0.5f, 1.0f);
+                    const float du = noiseU * factor, dv = noiseV * factor;
+                    u = u + du;
+                    v = v + dv;
+                }
+            }
+        }
+        dstU[o] = u;
+        dstV[o] = v;
+    }
+}

@@ -1014,6 +1014,11 @@ static int adv_tile_attrs(fb_handle *h)
     CK(cudaFuncSetAttribute(k_advect_velocity_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     CK(cudaFuncSetAttribute(k_bfecc_velocity_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BSMEM));
     CK(cudaFuncSetAttribute(k_bfecc_velocity_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BSMEM));
+    CK(cudaFuncSetAttribute(k_confine_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_CSMEM));
+    CK(cudaFuncSetAttribute(k_advect_smoke_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SSMEM));
+    CK(cudaFuncSetAttribute(k_advect_smoke_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SSMEM));
+    CK(cudaFuncSetAttribute(k_bfecc_smoke_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SBSMEM));
+    CK(cudaFuncSetAttribute(k_bfecc_smoke_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SBSMEM));
     h->adv_tile_attr_set = true;
     return FB_OK;
 }
@@ -1027,6 +1032,26 @@ static const bool adv_full = getenv("FLUIDB200_ADV_FULL") != nullptr;
         if (h->cfg.nranks > 1) k_advect_velocity_tile<true><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, _tU, _tV, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         else k_advect_velocity_tile<false><<<_grid, AT_THREADS, AT_SMEM, h->stream>>>(c, _tU, _tV, sU, sV, mk, h->tile_flags, h->tile_ntx, aU, aV, oU, oV, dt, ib, ie, bad); \
         CKL("k_advect_velocity_tile"); } while (0)
+// advectSmoke / the BFECC smoke correct pass on tiles; the diffusion term (viscosityDiffusion > 0) stays with the round-1 kernel
+#define ADV_SMOKE_LAUNCH(c, sU, sV, mk, sM, shM, oM, dt, sa, visc, ib, ie, bad) do { \
+        if (adv_full || (visc) > 0.0f) { ADV_LAUNCH(k_advect_smoke_full, c, sU, sV, mk, sM, shM, oM, dt, sa, visc, ib, ie, bad); break; } \
+        TRY(adv_tile_attrs(h)); \
+        CUtensorMap _tU, _tV, _tM; TRY(tile_tmap(h, sU, AT_SVL, &_tU)); TRY(tile_tmap(h, sV, AT_SVL, &_tV)); TRY(tile_tmap(h, sM, AT_STL, &_tM)); \
+        ProfScope _ks(h, FB_PROF_K_ADVECT_SMOKE); \
+        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_STI) - (ib) / AT_STI, 1); \
+        if (h->cfg.nranks > 1) k_advect_smoke_tile<true><<<_grid, AT_THREADS, AT_SSMEM, h->stream>>>(c, _tU, _tV, _tM, sM, mk, h->tile_flags, h->tile_ntx, shM, oM, dt, sa, ib, ie, bad); \
+        else k_advect_smoke_tile<false><<<_grid, AT_THREADS, AT_SSMEM, h->stream>>>(c, _tU, _tV, _tM, sM, mk, h->tile_flags, h->tile_ntx, shM, oM, dt, sa, ib, ie, bad); \
+        CKL("k_advect_smoke_tile"); } while (0)
+#define ADV_BFECC_SMOKE_LAUNCH(c, sU, sV, mk, oM, fM, cM, dt, sa, ib, ie, bad) do { \
+        if (adv_full) { ADV_LAUNCH(k_bfecc_smoke_correct, c, sU, sV, mk, oM, fM, cM, dt, sa, ib, ie, bad); break; } \
+        TRY(adv_tile_attrs(h)); \
+        CUtensorMap _tU, _tV, _tO, _tF; \
+        TRY(tile_tmap(h, sU, AT_SVL, &_tU)); TRY(tile_tmap(h, sV, AT_SVL, &_tV)); TRY(tile_tmap(h, oM, AT_SVL, &_tO)); TRY(tile_tmap(h, fM, AT_STL, &_tF)); \
+        ProfScope _ks(h, FB_PROF_K_BFECC_SMOKE); \
+        const dim3 _grid(h->tile_ntx, cdiv(ie, AT_STI) - (ib) / AT_STI, 1); \
+        if (h->cfg.nranks > 1) k_bfecc_smoke_tile<true><<<_grid, AT_THREADS, AT_SBSMEM, h->stream>>>(c, _tU, _tV, _tO, _tF, fM, mk, h->tile_flags, h->tile_ntx, cM, dt, sa, ib, ie, bad); \
+        else k_bfecc_smoke_tile<false><<<_grid, AT_THREADS, AT_SBSMEM, h->stream>>>(c, _tU, _tV, _tO, _tF, fM, mk, h->tile_flags, h->tile_ntx, cM, dt, sa, ib, ie, bad); \
+        CKL("k_bfecc_smoke_tile"); } while (0)
 #define ADV_BFECC_VELOCITY_LAUNCH(c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad) do { \
         if (adv_full) { ADV_LAUNCH(k_bfecc_velocity_correct, c, sU, sV, mk, fU, fV, oU, oV, dt, ib, ie, bad); break; } \
         TRY(adv_tile_attrs(h)); \
@@ -1257,9 +1282,20 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
     dim3 grid(cdiv(g.NY, CT_J), cdiv(ie - ib, CT_I), 1);
     volatile float ts = do_turb ? p->turbulence_strength * dt : 0.0f;
     ProfScope _ks(h, FB_PROF_K_CONFINE_TURBULENCE);
-    k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
-                                                                do_confine ? p->confinement : 0.0f, ts, ib, ie);
-    CKL("k_confine_turbulence");
+    if (adv_full) {
+        k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
+                                                                    do_confine ? p->confinement : 0.0f, ts, ib, ie);
+        CKL("k_confine_turbulence");
+    } else {
+        TRY(adv_tile_attrs(h));
+        CUtensorMap tU, tV;
+        TRY(tile_tmap(h, h->f[FB_U], AT_CVL, &tU)); TRY(tile_tmap(h, h->f[FB_V], AT_CVL, &tV));
+        const AdvCtx c = adv_ctx(h);
+        const dim3 tgrid(h->tile_ntx, cdiv(ie, AT_CTI) - ib / AT_CTI, 1);
+        k_confine_tile<<<tgrid, AT_THREADS, AT_CSMEM, h->stream>>>(c, tU, tV, h->mask, nU, nV, dU, dV, h->cfg.h, dt,
+                                                                  do_confine ? p->confinement : 0.0f, ts, ib, ie, h->d_bad);
+        CKL("k_confine_tile");
+    }
     give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]);
     h->f[FB_U] = dU; h->f[FB_V] = dV;
     return FB_OK;
@@ -1287,8 +1323,8 @@ static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt, int ext
     TRY(take_plane(h, &dM));
     int ib, ie; range(h, ext, ib, ie);
     const AdvCtx c = adv_ctx(h);
-    ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
-               p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
+                     p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
     give_plane(h, h->f[FB_M]);
     h->f[FB_M] = dM;
     TRY(sync_shadow(h, FB_M, FB_NEWM));
@@ -1325,14 +1361,14 @@ static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt, i
     TRY(take_plane(h, &fM)); TRY(take_plane(h, &cM));
     int ib, ie; range(h, ext_fwd, ib, ie);
     const AdvCtx c = adv_ctx(h);
-    ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], fM, dt,
-               p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], fM, dt,
+                     p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
     range(h, ext_corr, ib, ie);
-    ADV_LAUNCH(k_bfecc_smoke_correct, c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, p->smoke_advection, ib, ie, h->d_bad);
+    ADV_BFECC_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, p->smoke_advection, ib, ie, h->d_bad);
     float *oM = h->f[FB_M];
     range(h, 0, ib, ie);
-    ADV_LAUNCH(k_advect_smoke_full, c, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
-               p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
+                     p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
     give_plane(h, fM); give_plane(h, cM);
     TRY(sync_shadow(h, FB_M, FB_NEWM));
     return FB_OK;
