@@ -635,31 +635,35 @@ k_bfecc_smoke_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, cons
 #define AT_CTI 16
 #endif
 #define AT_CVL (AT_CTI + 4)                  // staged lines of U, V
+#define AT_CML (AT_CTI + 2)                  // staged lines of the mask (bytes; AT_PW columns like the planes)
 #define AT_CW 132                            // curl tile pitch: columns j0 - 1 .. j0 + 128 (+ padding)
-#define AT_CSMEM (2 * AT_CVL * AT_PW * 4 + (AT_CTI + 2) * AT_CW * 4 + 16)
+#define AT_CMB ((AT_CML * AT_PW + 127) / 128 * 128)
+#define AT_CSMEM (2 * AT_CVL * AT_PW * 4 + AT_CMB + AT_CML * AT_CW * 4 + 16)
 
-__device__ __forceinline__ float at_curl(const AdvCtx &c, const float *__restrict__ sU, const float *__restrict__ sV, const int ls0, const int cs0,
-                                         const unsigned char *__restrict__ mask, const int i, const int j, const float h)
+// curl of cell (i, j) (fluid.go:453-466) from the staged tiles; `ok` = the cell lies in 1..NumX-2 x 1..NumY-2 with both
+// neighbouring lines resident
+__device__ __forceinline__ float at_curl(const float *__restrict__ pu, const float *__restrict__ pv, const unsigned m, const bool ok, const float h)
 {
-    if (i < 1 || i > c.NX - 2 || j < 1 || j > c.NY - 2) return 0.0f;
-    if (i - 1 < c.i_alloc0 || i + 1 >= c.i_alloc0 + c.lines_alloc) return 0.0f;
-    if (!(mask[(size_t)(i - c.i_alloc0) * c.pitch + j] & MK_C)) return 0.0f;
-    const float *pu = sU + (i - ls0) * AT_PW + (j - cs0), *pv = sV + (i - ls0) * AT_PW + (j - cs0);
-    const float dvdx = div0((pv[AT_PW] - pv[-AT_PW]) * 0.5f, h);
-    const float dudy = div0((pu[1] - pu[-1]) * 0.5f, h);
-    return dvdx - dudy;
+    float cu = 0.0f;
+    if (ok && (m & MK_C)) {
+        const float dvdx = div0((pv[AT_PW] - pv[-AT_PW]) * 0.5f, h);
+        const float dudy = div0((pu[1] - pu[-1]) * 0.5f, h);
+        cu = dvdx - dudy;
+    }
+    return cu;
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 6)
 k_confine_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
-               const unsigned char *__restrict__ mask, const float *__restrict__ nU, const float *__restrict__ nV,
+               const __grid_constant__ CUtensorMap tmMask, const float *__restrict__ nU, const float *__restrict__ nV,
                float *__restrict__ dstU, float *__restrict__ dstV, const float h, const float dt, const float confinement,
                const float turbStrength, const int ib, const int ie, int *bad)
 {
     extern __shared__ __align__(128) unsigned char at_smem[];
     float *sU = reinterpret_cast<float *>(at_smem), *sV = sU + AT_CVL * AT_PW;
-    float *sC = sV + AT_CVL * AT_PW;                               // [AT_CTI + 2][AT_CW]: lines t0 - 1 .., columns j0 - 1 ..
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sC + (AT_CTI + 2) * AT_CW);
+    unsigned char *sMk = reinterpret_cast<unsigned char *>(sV + AT_CVL * AT_PW);      // [AT_CML][AT_PW]: lines t0 - 1 .., columns j0 - 8 ..
+    float *sC = reinterpret_cast<float *>(sMk + AT_CMB);           // [AT_CML][AT_CW]: lines t0 - 1 .., columns j0 - 1 ..
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sC + AT_CML * AT_CW);
     const int tid = threadIdx.x;
     const int ty = ib / AT_CTI + blockIdx.y, tx = blockIdx.x;
     const int t0 = ty * AT_CTI, j0 = tx * AT_TJ;
@@ -670,21 +674,30 @@ k_confine_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __
     __syncthreads();
     if (tid == 0) {
         const unsigned b = rq_s32(bar);
-        rq_mbar_expect_tx(bar, 2u * AT_CVL * AT_PW * 4u);
+        rq_mbar_expect_tx(bar, 2u * AT_CVL * AT_PW * 4u + AT_CML * AT_PW);
         at_tensor_load(sU, &tmU, cs0, ls0 - c.i_alloc0, b);
         at_tensor_load(sV, &tmV, cs0, ls0 - c.i_alloc0, b);
+        at_tensor_load(reinterpret_cast<float *>(sMk), &tmMask, cs0, t0 - 1 - c.i_alloc0, b);
     }
     at_wait_tiles(bar, 0, bad);
     const int cl = tid & 127, grp = tid >> 7;
     const int j = j0 + cl;
+    const bool colok = j >= 1 && j <= c.NY - 2;
     if (confinement != 0.0f) {
         // curl of lines t0 - 1 .. t0 + AT_CTI, columns j0 - 1 .. j0 + 128: a lane per column, the two edge columns on the side
-        constexpr int CL = (AT_CTI + 2 + AT_LG - 1) / AT_LG;       // curl lines per line group
-        for (int li = grp * CL; li < min((grp + 1) * CL, AT_CTI + 2); li++)
-            sC[li * AT_CW + cl + 1] = at_curl(c, sU, sV, ls0, cs0, mask, t0 - 1 + li, j, h);
-        if (tid < 2 * (AT_CTI + 2)) {
-            const int side = tid >= AT_CTI + 2, li = tid - side * (AT_CTI + 2);
-            sC[li * AT_CW + (side ? AT_TJ + 1 : 0)] = at_curl(c, sU, sV, ls0, cs0, mask, t0 - 1 + li, side ? j0 + AT_TJ : j0 - 1, h);
+        constexpr int CL = (AT_CML + AT_LG - 1) / AT_LG;           // curl lines per line group
+        for (int li = grp * CL; li < min((grp + 1) * CL, AT_CML); li++) {
+            const int i = t0 - 1 + li;
+            const bool lineok = i >= 1 && i <= c.NX - 2 && i - 1 >= c.i_alloc0 && i + 1 < c.i_alloc0 + c.lines_alloc;
+            const int o = (i - ls0) * AT_PW + (j - cs0);
+            sC[li * AT_CW + cl + 1] = at_curl(sU + o, sV + o, sMk[li * AT_PW + (j - cs0)], lineok && colok, h);
+        }
+        if (tid < 2 * AT_CML) {
+            const int side = tid >= AT_CML, li = tid - side * AT_CML;
+            const int i = t0 - 1 + li, jj = side ? j0 + AT_TJ : j0 - 1;
+            const bool ok = i >= 1 && i <= c.NX - 2 && i - 1 >= c.i_alloc0 && i + 1 < c.i_alloc0 + c.lines_alloc && jj >= 1 && jj <= c.NY - 2;
+            const int o = (i - ls0) * AT_PW + (jj - cs0);
+            sC[li * AT_CW + (side ? AT_TJ + 1 : 0)] = at_curl(sU + o, sV + o, sMk[li * AT_PW + (jj - cs0)], ok, h);
         }
         __syncthreads();
     }
@@ -694,7 +707,7 @@ k_confine_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __
     for (int i = ia; i < ibb; i++) {
         const size_t o = (size_t)(i - c.i_alloc0) * c.pitch + j;
         float u = sU[(i - ls0) * AT_PW + (j - cs0)], v = sV[(i - ls0) * AT_PW + (j - cs0)];
-        if (i >= 1 && i <= c.NX - 2 && j >= 1 && j <= c.NY - 2 && (mask[o] & MK_C)) {
+        if (i >= 1 && i <= c.NX - 2 && colok && (sMk[(i - t0 + 1) * AT_PW + (j - cs0)] & MK_C)) {
             if (confinement != 0.0f) {
                 const float eps = 1e-5f;
                 const float *pc = sC + (i - t0 + 1) * AT_CW + (cl + 1);
