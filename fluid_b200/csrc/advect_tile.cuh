@@ -635,10 +635,9 @@ k_bfecc_smoke_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, cons
 #define AT_CTI 16
 #endif
 #define AT_CVL (AT_CTI + 4)                  // staged lines of U, V
-#define AT_CML (AT_CTI + 2)                  // staged lines of the mask (bytes; AT_PW columns like the planes)
+#define AT_CML (AT_CTI + 2)                  // lines of the curl tile
 #define AT_CW 132                            // curl tile pitch: columns j0 - 1 .. j0 + 128 (+ padding)
-#define AT_CMB ((AT_CML * AT_PW + 127) / 128 * 128)
-#define AT_CSMEM (2 * AT_CVL * AT_PW * 4 + AT_CMB + AT_CML * AT_CW * 4 + 16)
+#define AT_CSMEM (2 * AT_CVL * AT_PW * 4 + AT_CML * AT_CW * 4 + 16)
 
 // curl of cell (i, j) (fluid.go:453-466) from the staged tiles; `ok` = the cell lies in 1..NumX-2 x 1..NumY-2 with both
 // neighbouring lines resident
@@ -655,14 +654,13 @@ __device__ __forceinline__ float at_curl(const float *__restrict__ pu, const flo
 
 __global__ void __launch_bounds__(AT_THREADS, 6)
 k_confine_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV,
-               const __grid_constant__ CUtensorMap tmMask, const float *__restrict__ nU, const float *__restrict__ nV,
+               const unsigned char *__restrict__ mask, const float *__restrict__ nU, const float *__restrict__ nV,
                float *__restrict__ dstU, float *__restrict__ dstV, const float h, const float dt, const float confinement,
                const float turbStrength, const int ib, const int ie, int *bad)
 {
     extern __shared__ __align__(128) unsigned char at_smem[];
     float *sU = reinterpret_cast<float *>(at_smem), *sV = sU + AT_CVL * AT_PW;
-    unsigned char *sMk = reinterpret_cast<unsigned char *>(sV + AT_CVL * AT_PW);      // [AT_CML][AT_PW]: lines t0 - 1 .., columns j0 - 8 ..
-    float *sC = reinterpret_cast<float *>(sMk + AT_CMB);           // [AT_CML][AT_CW]: lines t0 - 1 .., columns j0 - 1 ..
+    float *sC = sV + AT_CVL * AT_PW;                               // [AT_CML][AT_CW]: lines t0 - 1 .., columns j0 - 1 ..
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(sC + AT_CML * AT_CW);
     const int tid = threadIdx.x;
     const int ty = ib / AT_CTI + blockIdx.y, tx = blockIdx.x;
@@ -674,40 +672,61 @@ k_confine_tile(const AdvCtx c, const __grid_constant__ CUtensorMap tmU, const __
     __syncthreads();
     if (tid == 0) {
         const unsigned b = rq_s32(bar);
-        rq_mbar_expect_tx(bar, 2u * AT_CVL * AT_PW * 4u + AT_CML * AT_PW);
+        rq_mbar_expect_tx(bar, 2u * AT_CVL * AT_PW * 4u);
         at_tensor_load(sU, &tmU, cs0, ls0 - c.i_alloc0, b);
         at_tensor_load(sV, &tmV, cs0, ls0 - c.i_alloc0, b);
-        at_tensor_load(reinterpret_cast<float *>(sMk), &tmMask, cs0, t0 - 1 - c.i_alloc0, b);
     }
-    at_wait_tiles(bar, 0, bad);
     const int cl = tid & 127, grp = tid >> 7;
     const int j = j0 + cl;
     const bool colok = j >= 1 && j <= c.NY - 2;
+    // the mask bytes of this thread's column for the lines it touches (curl lines t0 - 1 + grp * CL .., which contain its
+    // cells), fetched while the tiles are in flight
+    constexpr int CL = (AT_CML + AT_LG - 1) / AT_LG;               // curl lines per line group
+    unsigned mk[CL];
+#pragma unroll
+    for (int q = 0; q < CL; q++) {
+        const int i = t0 - 1 + grp * CL + q;
+        mk[q] = (colok && i >= max(c.i_alloc0, 0) && i < min(c.i_alloc0 + c.lines_alloc, c.NX)) ? mask[(size_t)(i - c.i_alloc0) * c.pitch + j] : 0u;
+    }
+    unsigned mside = 0;
+    if (tid < 2 * AT_CML) {
+        const int side = tid >= AT_CML, i = t0 - 1 + (tid - side * AT_CML), jj = side ? j0 + AT_TJ : j0 - 1;
+        if (jj >= 1 && jj <= c.NY - 2 && i >= max(c.i_alloc0, 0) && i < min(c.i_alloc0 + c.lines_alloc, c.NX)) mside = mask[(size_t)(i - c.i_alloc0) * c.pitch + jj];
+    }
+    at_wait_tiles(bar, 0, bad);
     if (confinement != 0.0f) {
         // curl of lines t0 - 1 .. t0 + AT_CTI, columns j0 - 1 .. j0 + 128: a lane per column, the two edge columns on the side
-        constexpr int CL = (AT_CML + AT_LG - 1) / AT_LG;           // curl lines per line group
-        for (int li = grp * CL; li < min((grp + 1) * CL, AT_CML); li++) {
-            const int i = t0 - 1 + li;
-            const bool lineok = i >= 1 && i <= c.NX - 2 && i - 1 >= c.i_alloc0 && i + 1 < c.i_alloc0 + c.lines_alloc;
-            const int o = (i - ls0) * AT_PW + (j - cs0);
-            sC[li * AT_CW + cl + 1] = at_curl(sU + o, sV + o, sMk[li * AT_PW + (j - cs0)], lineok && colok, h);
+#pragma unroll
+        for (int q = 0; q < CL; q++) {
+            const int li = grp * CL + q, i = t0 - 1 + li;
+            if (li < AT_CML) {
+                const bool lineok = i >= 1 && i <= c.NX - 2 && i - 1 >= c.i_alloc0 && i + 1 < c.i_alloc0 + c.lines_alloc;
+                const int o = (i - ls0) * AT_PW + (j - cs0);
+                sC[li * AT_CW + cl + 1] = at_curl(sU + o, sV + o, mk[q], lineok && colok, h);
+            }
         }
         if (tid < 2 * AT_CML) {
             const int side = tid >= AT_CML, li = tid - side * AT_CML;
             const int i = t0 - 1 + li, jj = side ? j0 + AT_TJ : j0 - 1;
             const bool ok = i >= 1 && i <= c.NX - 2 && i - 1 >= c.i_alloc0 && i + 1 < c.i_alloc0 + c.lines_alloc && jj >= 1 && jj <= c.NY - 2;
             const int o = (i - ls0) * AT_PW + (jj - cs0);
-            sC[li * AT_CW + (side ? AT_TJ + 1 : 0)] = at_curl(sU + o, sV + o, sMk[li * AT_PW + (jj - cs0)], ok, h);
+            sC[li * AT_CW + (side ? AT_TJ + 1 : 0)] = at_curl(sU + o, sV + o, mside, ok, h);
         }
         __syncthreads();
     }
     if (j >= c.NY) return;
     constexpr int half = AT_CTI / AT_LG;
-    const int ia = max(t0 + grp * half, i0), ibb = min(t0 + (grp + 1) * half, i1);
-    for (int i = ia; i < ibb; i++) {
+    static_assert(AT_CTI % AT_LG == 0 && half + 1 <= CL, "a thread's cells lie inside its curl lines");
+#pragma unroll
+    for (int q = 0; q < half; q++) {
+        const int i = t0 + grp * half + q;
+        if (i < i0 || i >= i1) continue;
         const size_t o = (size_t)(i - c.i_alloc0) * c.pitch + j;
         float u = sU[(i - ls0) * AT_PW + (j - cs0)], v = sV[(i - ls0) * AT_PW + (j - cs0)];
-        if (i >= 1 && i <= c.NX - 2 && colok && (sMk[(i - t0 + 1) * AT_PW + (j - cs0)] & MK_C)) {
+        // line i is curl line (i - t0 + 1) = grp * half + q + 1; this thread's curl lines start at grp * CL
+        static_assert(AT_LG == 2 && CL == half + 1, "index arithmetic below");
+        const unsigned m = grp ? mk[q] : mk[q + 1];        // (static indices: the array stays in registers)
+        if (i >= 1 && i <= c.NX - 2 && colok && (m & MK_C)) {
             if (confinement != 0.0f) {
                 const float eps = 1e-5f;
                 const float *pc = sC + (i - t0 + 1) * AT_CW + (cl + 1);

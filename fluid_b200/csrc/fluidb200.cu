@@ -1007,34 +1007,6 @@ static int tile_tmap(fb_handle *h, const float *plane, int box_lines, CUtensorMa
     return FB_OK;
 }
 
-// the neighbour mask as a 2-D uint8 tensor map (box_lines x AT_PW bytes)
-static int tile_tmap_mask(fb_handle *h, int box_lines, CUtensorMap *out)
-{
-    const auto key = std::make_pair((const void *)h->mask, -box_lines);
-    auto it = h->tmaps.find(key);
-    if (it != h->tmaps.end()) { *out = it->second; return FB_OK; }
-    static PFN_cuTensorMapEncodeTiled encode = nullptr;
-    if (!encode) {
-        cudaDriverEntryPointQueryResult q;
-        void *fn = nullptr;
-        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (!fn || q != cudaDriverEntryPointSuccess) return fail(h, FB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
-    }
-    const Grid &g = h->g;
-    const cuuint64_t dims[2] = { (cuuint64_t)g.pitch, (cuuint64_t)g.lines_alloc };
-    const cuuint64_t strides[1] = { (cuuint64_t)g.pitch };
-    const cuuint32_t box[2] = { (cuuint32_t)AT_PW, (cuuint32_t)box_lines };
-    const cuuint32_t estr[2] = { 1, 1 };
-    CUtensorMap tm;
-    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->mask, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(h, FB_ERR_CUDA, "cuTensorMapEncodeTiled (mask) failed");
-    h->tmaps[key] = tm;
-    *out = tm;
-    return FB_OK;
-}
-
 static int adv_tile_attrs(fb_handle *h)
 {
     if (h->adv_tile_attr_set) return FB_OK;
@@ -1316,11 +1288,11 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
         CKL("k_confine_turbulence");
     } else {
         TRY(adv_tile_attrs(h));
-        CUtensorMap tU, tV, tM;
-        TRY(tile_tmap(h, h->f[FB_U], AT_CVL, &tU)); TRY(tile_tmap(h, h->f[FB_V], AT_CVL, &tV)); TRY(tile_tmap_mask(h, AT_CML, &tM));
+        CUtensorMap tU, tV;
+        TRY(tile_tmap(h, h->f[FB_U], AT_CVL, &tU)); TRY(tile_tmap(h, h->f[FB_V], AT_CVL, &tV));
         const AdvCtx c = adv_ctx(h);
         const dim3 tgrid(h->tile_ntx, cdiv(ie, AT_CTI) - ib / AT_CTI, 1);
-        k_confine_tile<<<tgrid, AT_THREADS, AT_CSMEM, h->stream>>>(c, tU, tV, tM, nU, nV, dU, dV, h->cfg.h, dt,
+        k_confine_tile<<<tgrid, AT_THREADS, AT_CSMEM, h->stream>>>(c, tU, tV, h->mask, nU, nV, dU, dV, h->cfg.h, dt,
                                                                   do_confine ? p->confinement : 0.0f, ts, ib, ie, h->d_bad);
         CKL("k_confine_tile");
     }
