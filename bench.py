@@ -896,8 +896,10 @@ def run_preset(args, workload, rank, world, local, primary):
     if world > 1:
         sim.check_halo()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        residual = residual_on_state(sim, preset, fluid_b200)
-        r = cpu_reference_run(workload, 2, 1, budget_s=60.0)
+        big = cells_total > 2.0e7          # the oracle needs ~0.4 us per cell-step: 16386^2 would take minutes per step
+        if not big:
+            residual = residual_on_state(sim, preset, fluid_b200)
+        r = cpu_reference_run(workload, 2, 1, sample_size=(4096, 4096) if big else None, budget_s=60.0)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "grid", "same_grid_as_gpu_arm")}
         cpu["go_toolchain"] = go_probe()
         cpu["config1_anchor"] = cpu_anchor_config1()

@@ -1281,8 +1281,12 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
     int ib, ie; range(h, ext, ib, ie);
     dim3 grid(cdiv(g.NY, CT_J), cdiv(ie - ib, CT_I), 1);
     volatile float ts = do_turb ? p->turbulence_strength * dt : 0.0f;
+    // k_confine_tile (TMA-staged tiles, lane per cell) measured SLOWER than this kernel (0.158 against 0.148 ms with
+    // confinement, 0.065 against ~0.05 turbulence only): the pass is division / square-root bound and four cells per thread
+    // give it the instruction-level parallelism a lane per cell lacks.  FLUIDB200_CONFINE_TILE=1 selects the tile form (A/B).
+    static const bool confine_tile = getenv("FLUIDB200_CONFINE_TILE") != nullptr;
     ProfScope _ks(h, FB_PROF_K_CONFINE_TURBULENCE);
-    if (adv_full) {
+    if (adv_full || !confine_tile) {
         k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
                                                                     do_confine ? p->confinement : 0.0f, ts, ib, ie);
         CKL("k_confine_turbulence");
