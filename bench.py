@@ -503,7 +503,7 @@ def residual_on_state(sim, preset, fluid_b200):
                     "8 sweeps (fluid.go:157-234); gpu = the benchmarked solver, 8 iterations; MaxDivergence() of fluid.go:876"}
 
 
-def slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, transport):
+def slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, transport, overlap):
     """N ranks vs one GPU on the same small preset (Karman, BFECC + confinement, pressure-form solver): every field must
     be bit-identical.  Runs inside the driver's own SCALE invocation so that N-process correctness is on record."""
     from fluid_b200 import presets
@@ -516,6 +516,7 @@ def slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, tra
     sim.edit(p.init)
     sim.UseBFECC = True
     sim.Confinement = 0.1
+    sim.set_overlap(overlap)
     sim.step(p.dt, steps, p.per_step)
     sim.check_halo()
     got = {k: sim.get(k) for k in ("U", "V", "M", "p")}
@@ -530,8 +531,9 @@ def slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, tra
         diffs = {k: float(np.max(np.abs(got[k].astype(np.float64) - one.get(k).astype(np.float64)))) for k in got}
         one.close()
         out = {"ok": all(v == 0.0 for v in diffs.values()), "max_abs_diff": diffs, "ranks": world, "grid": [width + 2, height + 2],
-               "steps": steps, "what": "Karman preset, BFECC + confinement, pressure-form solver: N row slabs (peer-memory halo "
-                                        "exchange) vs the single-GPU run of the same grid, U V M p compared bit for bit"}
+               "steps": steps, "overlapped_exchange": bool(overlap),
+               "what": "Karman preset, BFECC + confinement, pressure-form solver: N row slabs (peer-memory halo exchange, as "
+                       "benchmarked) vs the single-GPU run of the same grid, U V M p compared bit for bit"}
     if world > 1:
         dist.barrier()
     return out
@@ -572,11 +574,15 @@ def run_preset(args, workload, rank, world, local, primary):
         sim.UseBFECC = bfecc
         sim.Confinement = conf
         sim.adaptive_reach = True       # reach (hence the ghost lines every phase recomputes) follows the all-reduced max |u|
+        overlap = args.transport == "peer" and not args.no_overlap
+        sim.set_overlap(overlap)        # the exchange for step k+1 rides inside step k (FB_OPT_HALO_OVERLAP)
         cells_total = sim.global_cells
         how = ("pulled from the neighbours' CUDA-IPC send buffers over NVLink (flag in peer memory, no collective)"
                if args.transport == "peer" else "NCCL send/recv")
+        when = ("overlapped with the step: U, V travel on a second stream during the smoke passes, M during the interior of the last "
+                "smoke pass, whose boundary strips are computed first" if overlap else "in front of the step")
         parallelism = (f"row slabs over i, {world} ranks, {ghost} ghost lines allocated (reach for |u| <= 8), the reach used per step "
-                       f"re-measured every 16 steps from the all-reduced max |u| x 1.5; 1 halo exchange per step {how}")
+                       f"re-measured every 16 steps from the all-reduced max |u| x 1.5; 1 halo exchange per step {how}, {when}")
     else:
         sim = make_fluid(fluid_b200, preset, solver, device=local)
         cells_total = sim.NumX * sim.NumY
@@ -641,8 +647,11 @@ def run_preset(args, workload, rank, world, local, primary):
                         "k_advect_smoke_full": 20, "k_bfecc_smoke_correct": 24, "k_confine_turbulence": 20}
     kernel_real = {"k_pressure_solve": {"pressure": "k_rbq_stream" if os.environ.get("FLUIDB200_RBQ_STREAM") else "k_rbq_fused",
                                         "redblack": "k_rb_fused", "exact": "k_gs_wavefront"}[args.solver],
-                   "k_advect_velocity_full": "k_advect_velocity_full" if os.environ.get("FLUIDB200_ADV_FULL") else "k_advect_velocity_tile",
-                   "k_bfecc_velocity_correct": "k_bfecc_velocity_correct" if os.environ.get("FLUIDB200_ADV_FULL") else "k_bfecc_velocity_tile"}
+                   "k_confine_turbulence": ("k_confine_tile" if os.environ.get("FLUIDB200_CONFINE_TILE") else
+                                            "k_confine_turbulence" if os.environ.get("FLUIDB200_CONFINE_IEEE") else "k_confine_fast")}
+    if not os.environ.get("FLUIDB200_ADV_FULL"):     # the slots are named after the round-1 kernels; what runs is the tile form
+        kernel_real.update({"k_advect_velocity_full": "k_advect_velocity_tile", "k_bfecc_velocity_correct": "k_bfecc_velocity_tile",
+                            "k_advect_smoke_full": "k_advect_smoke_tile", "k_bfecc_smoke_correct": "k_bfecc_smoke_tile"})
     kern = {}
     for k in L.PROF_KERNELS:
         tot, calls = phases.get(k, (0.0, 0))
@@ -919,6 +928,7 @@ def main():
     ap.add_argument("--solver", default="pressure", choices=["pressure", "redblack", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="halo exchange between slabs (N > 1)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange halos in front of every step instead of inside it")
     ap.add_argument("--no-secondary", action="store_true", help="skip the e2e, other-solver, parity-check and config[3] legs")
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps that develop the flow (-1: the jet front crosses one GPU's lines)")
     ap.add_argument("--preroll-cap", type=int, default=1500)
@@ -965,7 +975,8 @@ def main():
         if world > 1:
             import fluid_b200
             from fluid_b200 import parallel
-            pc = slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, args.transport)
+            pc = slab_parity_check(fluid_b200, parallel, torch, dist, rank, world, local, args.transport,
+                                   args.transport == "peer" and not args.no_overlap)
             if rank == 0:
                 line["parity_check"] = pc
         if args.workload == "karman4096":

@@ -22,6 +22,7 @@ FIELD_NAMES = {"U": U, "V": V, "newU": NEWU, "newV": NEWV, "p": P, "S": S, "M": 
 # fb_solver
 SOLVER_EXACT, SOLVER_REDBLACK, SOLVER_REDBLACK_PRESSURE = 0, 1, 2
 OPT_SOLVE_STATS = 0
+OPT_HALO_OVERLAP = 1
 # fb_flags
 FLAG_LITERAL, FLAG_EXACT_SHADOW = 1, 2
 # fb_phase_id
@@ -101,6 +102,7 @@ SYMBOLS = {
     "fb_profile_read": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "fb_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "fb_launch_count": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
+    "fb_selftest_fastmath": (C.c_int, [C.c_int32, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(C.c_uint64)]),
     "fb_version": (C.c_int, []),
 }
 

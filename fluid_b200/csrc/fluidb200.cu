@@ -71,6 +71,11 @@ struct fb_handle {
     std::vector<int> h_alive;
     fb_handle *halo_peer_local[2];// same-process neighbours: their post is awaited with an event, not by spinning
     cudaEvent_t ev_halo;          // recorded after every post
+    // overlapped exchange inside fb_step_local (FB_OPT_HALO_OVERLAP): second stream, its events, its own epochs
+    bool halo_overlap;
+    cudaStream_t halo_stream;
+    cudaEvent_t ev_ovl_uv, ev_ovl_m, ev_ovl_done;
+    unsigned ovl_epoch_uv, ovl_epoch_m;
     bool prof;
     std::vector<cudaEvent_t> prof_pool;                 // recycled events
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pairs;
@@ -265,6 +270,10 @@ extern "C" int fb_destroy(fb_handle *h)
     if (h->d_particles) cudaFree(h->d_particles);
     if (h->d_alive) cudaFree(h->d_alive);
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+    if (h->halo_stream) {
+        cudaStreamSynchronize(h->halo_stream); cudaStreamDestroy(h->halo_stream);
+        cudaEventDestroy(h->ev_ovl_uv); cudaEventDestroy(h->ev_ovl_m); cudaEventDestroy(h->ev_ovl_done);
+    }
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_view) cudaEventDestroy(h->ev_view);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -285,10 +294,14 @@ extern "C" int fb_dims(const fb_handle *h, int64_t *nx, int64_t *ny, int64_t *i_
 }
 
 // ---- halo exchange through peer memory -----------------------------------------------------
-static inline size_t halo_total_bytes(const fb_handle *h) { return 2 * h->halo_buf_floats * sizeof(float) + 256; }
+// Four send buffers + 64 flag words: buffers 0 / 1 alternate for fb_halo_exchange (flag word 0 of the buffer), buffers 2 / 3
+// for the exchange overlapped with fb_step_local (word 1 = U, V posted, word 2 = M posted): either protocol's two-buffer
+// argument (kernels.cuh) holds on its own pair however the two are interleaved.
+#define HALO_NBUF 4
+static inline size_t halo_total_bytes(const fb_handle *h) { return HALO_NBUF * h->halo_buf_floats * sizeof(float) + 256; }
 static inline unsigned *halo_flags(const fb_handle *h, const float *base, int buf)
 {
-    return reinterpret_cast<unsigned *>(const_cast<float *>(base) + 2 * h->halo_buf_floats) + 16 * buf;
+    return reinterpret_cast<unsigned *>(const_cast<float *>(base) + HALO_NBUF * h->halo_buf_floats) + 16 * buf;
 }
 
 extern "C" int fb_halo_export(fb_handle *h, int32_t lines, void *ipc_handle64, uint64_t *device_ptr, size_t *bytes)
@@ -354,23 +367,47 @@ extern "C" int fb_halo_connect_local(fb_handle *h, int32_t side, fb_handle *peer
     return FB_OK;
 }
 
+// pack fields [field0, field0 + nf) of the boundary lines into send buffer `buf` and publish `epoch` in flag word `word`
+static int halo_post_fields(fb_handle *h, cudaStream_t st, int buf, int field0, int nf, int word, unsigned epoch)
+{
+    const Grid &g = h->g;
+    HaloPack a;
+    a.src[0] = h->f[FB_U]; a.src[1] = h->f[FB_V]; a.src[2] = h->f[FB_M];
+    a.dst = h->halo_send + (size_t)buf * h->halo_buf_floats;
+    a.i_lo = g.i_lo; a.i_hi = g.i_hi; a.lines = h->halo_lines; a.pitch = g.pitch; a.i_alloc0 = g.i_alloc0;
+    a.field0 = field0; a.nf = nf;
+    k_halo_pack<<<dim3(cdiv(g.pitch / 4, 256), h->halo_lines, 2 * nf), 256, 0, st>>>(a);
+    CKL("k_halo_pack");
+    k_halo_publish<<<1, 1, 0, st>>>(halo_flags(h, h->halo_send, buf) + word, epoch);
+    CKL("k_halo_publish");
+    return FB_OK;
+}
+// pull the same fields out of the connected neighbours' buffer `buf` once their flag word reached `epoch`
+static int halo_pull_fields(fb_handle *h, cudaStream_t st, int buf, int field0, int nf, int word, unsigned epoch)
+{
+    const Grid &g = h->g;
+    HaloPull a;
+    a.dst[0] = h->f[FB_U]; a.dst[1] = h->f[FB_V]; a.dst[2] = h->f[FB_M];
+    for (int sd = 0; sd < 2; sd++) {
+        a.peer[sd] = h->halo_peer[sd] ? h->halo_peer[sd] + (size_t)buf * h->halo_buf_floats : nullptr;
+        a.peer_flag[sd] = h->halo_peer[sd] ? halo_flags(h, h->halo_peer[sd], buf) + word : nullptr;
+    }
+    a.recv_i[0] = g.i_lo - h->halo_lines; a.recv_i[1] = g.i_hi;
+    a.lines = h->halo_lines; a.pitch = g.pitch; a.i_alloc0 = g.i_alloc0; a.epoch = epoch; a.bad = h->d_bad;
+    a.field0 = field0; a.nf = nf;
+    k_halo_pull<<<dim3(cdiv(g.pitch / 4, 256), h->halo_lines, 2 * nf), 256, 0, st>>>(a);
+    CKL("k_halo_pull");
+    return FB_OK;
+}
+
 // phase 1 of an exchange: pack the boundary lines and publish the epoch (never waits)
 extern "C" int fb_halo_post(fb_handle *h)
 {
     if (!h) return FB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (!h->halo_send) return fail(h, FB_ERR_INVALID, "fb_halo_post before fb_halo_export");
-    const Grid &g = h->g;
     h->halo_epoch++;
-    const int buf = (int)(h->halo_epoch & 1u);
-    HaloPack a;
-    a.src[0] = h->f[FB_U]; a.src[1] = h->f[FB_V]; a.src[2] = h->f[FB_M];
-    a.dst = h->halo_send + (size_t)buf * h->halo_buf_floats;
-    a.i_lo = g.i_lo; a.i_hi = g.i_hi; a.lines = h->halo_lines; a.pitch = g.pitch; a.i_alloc0 = g.i_alloc0;
-    k_halo_pack<<<dim3(cdiv(g.pitch / 4, 256), h->halo_lines, 6), 256, 0, h->stream>>>(a);
-    CKL("k_halo_pack");
-    k_halo_publish<<<1, 1, 0, h->stream>>>(halo_flags(h, h->halo_send, buf), h->halo_epoch);
-    CKL("k_halo_publish");
+    TRY(halo_post_fields(h, h->stream, (int)(h->halo_epoch & 1u), 0, 3, 0, h->halo_epoch));
     CK(cudaEventRecord(h->ev_halo, h->stream));
     return FB_OK;
 }
@@ -382,25 +419,43 @@ extern "C" int fb_halo_pull(fb_handle *h)
     CK(cudaSetDevice(h->device));
     if (!h->halo_send) return fail(h, FB_ERR_INVALID, "fb_halo_pull before fb_halo_export");
     if (!h->halo_peer[0] && !h->halo_peer[1]) return FB_OK;
-    const Grid &g = h->g;
-    const int buf = (int)(h->halo_epoch & 1u);
-    HaloPull a;
-    a.dst[0] = h->f[FB_U]; a.dst[1] = h->f[FB_V]; a.dst[2] = h->f[FB_M];
-    for (int sd = 0; sd < 2; sd++) {
-        a.peer[sd] = h->halo_peer[sd] ? h->halo_peer[sd] + (size_t)buf * h->halo_buf_floats : nullptr;
-        a.peer_flag[sd] = h->halo_peer[sd] ? halo_flags(h, h->halo_peer[sd], buf) : nullptr;
-    }
-    a.recv_i[0] = g.i_lo - h->halo_lines; a.recv_i[1] = g.i_hi;
-    a.lines = h->halo_lines; a.pitch = g.pitch; a.i_alloc0 = g.i_alloc0; a.epoch = h->halo_epoch; a.bad = h->d_bad;
     for (int sd = 0; sd < 2; sd++)
         if (h->halo_peer_local[sd]) {
             if (h->halo_peer_local[sd]->halo_epoch != h->halo_epoch)
                 return fail(h, FB_ERR_INVALID, "fb_halo_pull: a same-process neighbour has not posted this exchange yet");
             CK(cudaStreamWaitEvent(h->stream, h->halo_peer_local[sd]->ev_halo, 0));
         }
-    k_halo_pull<<<dim3(cdiv(g.pitch / 4, 256), h->halo_lines, 6), 256, 0, h->stream>>>(a);
-    CKL("k_halo_pull");
+    return halo_pull_fields(h, h->stream, (int)(h->halo_epoch & 1u), 0, 3, 0, h->halo_epoch);
+}
+
+// The exchange for the NEXT step, overlapped with the rest of this one (FB_OPT_HALO_OVERLAP; SURVEY.md 8e "boundary tiles
+// first").  U and V are final once the velocity advection is done: they are packed, published and the neighbours' lines pulled on
+// a second stream while the smoke passes run.  The last smoke pass is launched for the boundary strips first, then M takes the
+// same route while the interior lines are computed.  The pulls write ghost lines only.  Those of M are not read by anything still
+// running.  Those of U, V are read by the smoke passes inside the zone this rank recomputed itself (the reach), where the pulled
+// values are bit-identical to the local ones -- that identity is what makes N slabs equal one GPU -- and not outside it.
+static bool halo_overlap_on(const fb_handle *h)
+{
+    return h->halo_overlap && h->cfg.nranks > 1 && h->halo_send && (h->halo_peer[0] || h->halo_peer[1]) &&
+           !h->halo_peer_local[0] && !h->halo_peer_local[1];
+}
+static int halo_overlap_setup(fb_handle *h)
+{
+    if (h->halo_stream) return FB_OK;
+    CK(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_ovl_uv, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_ovl_m, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_ovl_done, cudaEventDisableTiming));
     return FB_OK;
+}
+// fields [field0, field0 + nf) are final on h->stream: exchange them on the second stream
+static int halo_overlap_fields(fb_handle *h, cudaEvent_t ev, int field0, int nf, int word, unsigned epoch)
+{
+    CK(cudaEventRecord(ev, h->stream));
+    CK(cudaStreamWaitEvent(h->halo_stream, ev, 0));
+    const int buf = 2 + (int)(epoch & 1u);
+    TRY(halo_post_fields(h, h->halo_stream, buf, field0, nf, word, epoch));
+    return halo_pull_fields(h, h->halo_stream, buf, field0, nf, word, epoch);
 }
 
 extern "C" int fb_halo_exchange(fb_handle *h)
@@ -465,6 +520,7 @@ extern "C" int fb_set_option(fb_handle *h, int32_t option, int32_t value)
 {
     if (!h) return FB_ERR_INVALID;
     if (option == FB_OPT_SOLVE_STATS) { h->want_stats = value != 0; return FB_OK; }
+    if (option == FB_OPT_HALO_OVERLAP) { h->halo_overlap = value != 0; return FB_OK; }
     return fail(h, FB_ERR_INVALID, "unknown option");
 }
 
@@ -488,6 +544,23 @@ extern "C" int fb_profile_read(fb_handle *h, float *ms, int32_t *calls)
         h->prof_pool.push_back(pr.second.second);
     }
     h->prof_pairs.clear();
+    return FB_OK;
+}
+
+// Diagnostics: div_fast / sqrt_fast of k_confine_fast against the IEEE instructions on n random operand sets.
+extern "C" int fb_selftest_fastmath(int32_t device, uint64_t n, uint32_t seed, int32_t mode, uint64_t *counts6)
+{
+    if (!counts6 || mode < 0 || mode > 3) return FB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return FB_ERR_CUDA;
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, 6 * sizeof(unsigned long long)) != cudaSuccess) return FB_ERR_CUDA;
+    cudaMemset(d, 0, 6 * sizeof(unsigned long long));
+    k_selftest_fastmath<<<148 * 8, 256>>>(n, seed, mode, d);
+    unsigned long long hcnt[6];
+    const cudaError_t e = cudaMemcpy(hcnt, d, sizeof(hcnt), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return FB_ERR_CUDA;
+    for (int k = 0; k < 6; k++) counts6[k] = hcnt[k];
     return FB_OK;
 }
 
@@ -1286,7 +1359,14 @@ static int confine_turbulence_fast(fb_handle *h, const fb_params *p, float dt, b
     // give it the instruction-level parallelism a lane per cell lacks.  FLUIDB200_CONFINE_TILE=1 selects the tile form (A/B).
     static const bool confine_tile = getenv("FLUIDB200_CONFINE_TILE") != nullptr;
     ProfScope _ks(h, FB_PROF_K_CONFINE_TURBULENCE);
-    if (adv_full || !confine_tile) {
+    // k_confine_fast: the same pass with the divisions / square roots as straight-line code (advect_fused.cuh); needs h inside
+    // the divisor range its sequences are exact for.  FLUIDB200_CONFINE_IEEE=1 keeps the IEEE-instruction kernel (A/B).
+    static const bool confine_ieee = getenv("FLUIDB200_CONFINE_IEEE") != nullptr;
+    if (!confine_ieee && !confine_tile && h->cfg.h >= FD_BLO && h->cfg.h < FD_HHI) {
+        k_confine_fast<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
+                                                              do_confine ? p->confinement : 0.0f, ts, ib, ie);
+        CKL("k_confine_fast");
+    } else if (adv_full || !confine_tile) {
         k_confine_turbulence<<<grid, CT_J * CT_I / 4, 0, h->stream>>>(g, h->f[FB_U], h->f[FB_V], h->mask, nU, nV, dU, dV, h->cfg.h, dt,
                                                                     do_confine ? p->confinement : 0.0f, ts, ib, ie);
         CKL("k_confine_turbulence");
@@ -1320,15 +1400,53 @@ static int advect_velocity_fast(fb_handle *h, float dt, int ext = 0)
     return FB_OK;
 }
 
-static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt, int ext = 0)
+// The pass that writes the step's final smoke field `outM` over the owned lines.  With `overlap` (fb_step_local,
+// FB_OPT_HALO_OVERLAP) the boundary strips -- the lines the neighbours will pull -- go first, the exchange of M starts on the
+// second stream, and the interior follows.
+static int halo_overlap_fields(fb_handle *h, cudaEvent_t ev, int field0, int nf, int word, unsigned epoch);
+static int smoke_final_pass(fb_handle *h, const fb_params *p, const AdvCtx &c, const float *srcM, float *outM, float dt, int ib, int ie,
+                            bool overlap)
+{
+    if (!overlap) {
+        ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, srcM, h->f[FB_NEWM], outM, dt,
+                         p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+        return FB_OK;
+    }
+    const Grid &g = h->g;
+    const int L = h->halo_lines;
+    int lo = ib, hi = ie;                      // what is left for the interior launch
+    if (h->halo_peer[0] && hi - lo > L) {
+        const int e = g.i_lo + L;
+        ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, srcM, h->f[FB_NEWM], outM, dt,
+                         p->smoke_advection, p->viscosity_diffusion, lo, e, h->d_bad);
+        lo = e;
+    }
+    if (h->halo_peer[1] && hi - lo > L) {
+        const int b = g.i_hi - L;
+        ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, srcM, h->f[FB_NEWM], outM, dt,
+                         p->smoke_advection, p->viscosity_diffusion, b, hi, h->d_bad);
+        hi = b;
+    }
+    const bool strips_done = (!h->halo_peer[0] || lo > ib) && (!h->halo_peer[1] || hi < ie);
+    float *const keepM = h->f[FB_M];
+    h->f[FB_M] = outM;                        // what the pack reads and the pull writes
+    if (strips_done) TRY(halo_overlap_fields(h, h->ev_ovl_m, 2, 1, 2, ++h->ovl_epoch_m));
+    if (hi > lo)
+        ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, srcM, h->f[FB_NEWM], outM, dt,
+                         p->smoke_advection, p->viscosity_diffusion, lo, hi, h->d_bad);
+    if (!strips_done) TRY(halo_overlap_fields(h, h->ev_ovl_m, 2, 1, 2, ++h->ovl_epoch_m));     // slab thinner than two strips
+    h->f[FB_M] = keepM;
+    return FB_OK;
+}
+
+static int advect_smoke_fast(fb_handle *h, const fb_params *p, float dt, int ext = 0, bool overlap = false)
 {
     TRY(ensure_mask(h));
     float *dM;
     TRY(take_plane(h, &dM));
     int ib, ie; range(h, ext, ib, ie);
     const AdvCtx c = adv_ctx(h);
-    ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], h->f[FB_NEWM], dM, dt,
-                     p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    TRY(smoke_final_pass(h, p, c, h->f[FB_M], dM, dt, ib, ie, overlap));
     give_plane(h, h->f[FB_M]);
     h->f[FB_M] = dM;
     TRY(sync_shadow(h, FB_M, FB_NEWM));
@@ -1358,7 +1476,7 @@ static int advect_velocity_bfecc_fast(fb_handle *h, float dt, int ext_fwd = 0, i
     return FB_OK;
 }
 
-static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt, int ext_fwd = 0, int ext_corr = 0)
+static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt, int ext_fwd = 0, int ext_corr = 0, bool overlap = false)
 {
     TRY(ensure_mask(h));
     float *fM, *cM;
@@ -1371,8 +1489,7 @@ static int advect_smoke_bfecc_fast(fb_handle *h, const fb_params *p, float dt, i
     ADV_BFECC_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, h->f[FB_M], fM, cM, dt, p->smoke_advection, ib, ie, h->d_bad);
     float *oM = h->f[FB_M];
     range(h, 0, ib, ie);
-    ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, cM, h->f[FB_NEWM], oM, dt,
-                     p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
+    TRY(smoke_final_pass(h, p, c, cM, oM, dt, ib, ie, overlap));
     give_plane(h, fM); give_plane(h, cM);
     TRY(sync_shadow(h, FB_M, FB_NEWM));
     return FB_OK;
@@ -1628,12 +1745,22 @@ extern "C" int fb_step_local(fb_handle *h, const fb_params *p, float dt, int32_t
         TRY(confine_turbulence_fast(h, p, dt, conf, turb, e_ct));
     }
     { ProfScope ps(h, FB_PROF_BORDERS); TRY(handle_borders(h, e_ct)); }
+    const bool ovl = multi && halo_overlap_on(h);
+    if (ovl) TRY(halo_overlap_setup(h));
     if (p->use_bfecc) {
         { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_bfecc_fast(h, dt, e_fwd, e_corr, e_final)); }
-        { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc_fast(h, p, dt, e_smoke_fwd, e_smoke_corr)); }
+        if (ovl) TRY(halo_overlap_fields(h, h->ev_ovl_uv, 0, 2, 1, ++h->ovl_epoch_uv));
+        { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_bfecc_fast(h, p, dt, e_smoke_fwd, e_smoke_corr, ovl)); }
     } else {
         { ProfScope ps(h, FB_PROF_ADVECT_VELOCITY); TRY(advect_velocity_fast(h, dt, e_final)); }
-        { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_fast(h, p, dt, 0)); }
+        if (ovl) TRY(halo_overlap_fields(h, h->ev_ovl_uv, 0, 2, 1, ++h->ovl_epoch_uv));
+        { ProfScope ps(h, FB_PROF_ADVECT_SMOKE); TRY(advect_smoke_fast(h, p, dt, 0, ovl)); }
+    }
+    if (ovl) {
+        // whatever is queued on the handle's stream next sees the refreshed ghost lines: the next fb_step_local needs no
+        // fb_halo_exchange (unless the host edits fields in between)
+        CK(cudaEventRecord(h->ev_ovl_done, h->halo_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_ovl_done, 0));
     }
     return FB_OK;   // ghost-zone violations are latched on the device: fb_check_halo
 }
@@ -1774,7 +1901,7 @@ extern "C" int fb_view(fb_handle *h, int32_t kind, float *out, float *min_value,
     default: return fail(h, FB_ERR_INVALID, "unknown view");
     }
     if (kind == FB_VIEW_SMOKE || kind == FB_VIEW_PRESSURE) {
-        k_minmax_all<<<grid, block, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
+        k_minmax_all<<<minmax_blocks(ie - ib), 256, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
         CKL("k_minmax_all");
     }
     CK(cudaMemcpyAsync(h->h_red + 32, h->d_red + 32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
@@ -1880,7 +2007,7 @@ extern "C" int fb_view_u8_begin(fb_handle *h, int32_t kind, int32_t stride, uint
     default: return fail(h, FB_ERR_INVALID, "unknown view");
     }
     if (kind == FB_VIEW_SMOKE || kind == FB_VIEW_PRESSURE) {
-        k_minmax_all<<<grid, block, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
+        k_minmax_all<<<minmax_blocks(ie - ib), 256, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
         CKL("k_minmax_all");
     }
     // owned lines whose global index is a multiple of stride: oi0 .. oi0 + ni - 1 (in units of stride)
@@ -1958,7 +2085,7 @@ extern "C" int fb_render_begin(fb_handle *h, int32_t kind, uint8_t *rgba_out, co
     default: return fail(h, FB_ERR_INVALID, "unknown view");
     }
     if (kind == FB_VIEW_SMOKE || kind == FB_VIEW_PRESSURE) {
-        k_minmax_all<<<grid, block, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
+        k_minmax_all<<<minmax_blocks(ie - ib), 256, 0, h->stream>>>(g, src, h->d_red + 32, ib, ie);
         CKL("k_minmax_all");
     }
     if (color_range) {

@@ -583,19 +583,37 @@ __device__ __forceinline__ void block_minmax(float lo, float hi, unsigned *red)
     }
 }
 
-// min/max over ALL cells of the dense array (pressure.go:8-15, smoke.go:8-15)
-__global__ void k_minmax_all(Grid g, const float *__restrict__ A, unsigned *red, int ib, int ie)
+// min/max over ALL cells of the dense array (pressure.go:8-15, smoke.go:8-15).  A block walks whole lines with float4
+// loads (every line starts 128-byte aligned, section 3 of DESIGN.md) and posts ONE pair of atomics: a block per 2 x 128
+// cells (round 1) spent its time on 131 k same-address atomics at 4098^2.  Launch: 1-D grid, 256 threads.
+__global__ void __launch_bounds__(256) k_minmax_all(Grid g, const float *__restrict__ A, unsigned *red, int ib, int ie)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = ib + blockIdx.y * blockDim.y + threadIdx.y;
     float lo = 3.402823466e+38f, hi = -3.402823466e+38f;
-    if (i < ie && j < g.NY) {
-        float v = A[g.at(i, j)];
-        if (v < lo) lo = v;
-        if (v > hi) hi = v;
+    const int nq = g.NY >> 2;
+    for (int i = ib + blockIdx.x; i < ie; i += gridDim.x) {
+        const float *row = A + g.at(i, 0);
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        for (int q = threadIdx.x; q < nq; q += 256) {
+            const float4 v = row4[q];
+            if (v.x < lo) lo = v.x;
+            if (v.x > hi) hi = v.x;
+            if (v.y < lo) lo = v.y;
+            if (v.y > hi) hi = v.y;
+            if (v.z < lo) lo = v.z;
+            if (v.z > hi) hi = v.z;
+            if (v.w < lo) lo = v.w;
+            if (v.w > hi) hi = v.w;
+        }
+        const int j = (nq << 2) + threadIdx.x;
+        if (j < g.NY) {
+            const float v = row[j];
+            if (v < lo) lo = v;
+            if (v > hi) hi = v;
+        }
     }
     block_minmax(lo, hi, red);
 }
+static inline int minmax_blocks(int lines) { return lines < 148 * 8 ? (lines > 0 ? lines : 1) : 148 * 8; }
 
 // Asynchronous views: sentinels of the min/max pair without a host copy, and a compact
 // (pitch -> NumY) snapshot of lines [ib, ie) fused with the min/max pass, so that the device
@@ -806,28 +824,29 @@ __global__ void k_edit_one(Grid g, EditFields f, fb_edit_cmd c)
 // pull waits on the neighbour's flag, so there is no host hand-shake and no collective; two
 // buffers alternate so that a rank may pack epoch k+2 only after its own pull of k+1, which the
 // neighbour's pack of k+1 (after ITS pull of k) precedes.
-struct HaloPack { const float *src[3]; float *dst; int i_lo, i_hi, lines, pitch, i_alloc0; };
+struct HaloPack { const float *src[3]; float *dst; int i_lo, i_hi, lines, pitch, i_alloc0, field0, nf; };
 __global__ void k_halo_pack(HaloPack a)
 {
-    // grid: (pitch/4 / 256, lines, 6): z = side * 3 + field
+    // grid: (pitch/4 / 256, lines, 2 * nf): z = side * nf + (field - field0); the buffer keeps room for all three fields
     const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y, side = blockIdx.z / 3, field = blockIdx.z % 3;
+    const int l = blockIdx.y, side = blockIdx.z / a.nf, field = a.field0 + blockIdx.z % a.nf;
     if (4 * c4 >= a.pitch) return;
     const int i = side == 0 ? a.i_lo + l : a.i_hi - a.lines + l;
     const float4 v = *reinterpret_cast<const float4 *>(a.src[field] + (size_t)(i - a.i_alloc0) * a.pitch + 4 * c4);
     *reinterpret_cast<float4 *>(a.dst + ((size_t)(side * 3 + field) * a.lines + l) * a.pitch + 4 * c4) = v;
 }
-__global__ void k_halo_publish(unsigned *flags, unsigned epoch)
+__global__ void k_halo_publish(unsigned *flag, unsigned epoch)
 {
     __threadfence_system();
-    reinterpret_cast<volatile unsigned *>(flags)[0] = epoch;
+    reinterpret_cast<volatile unsigned *>(flag)[0] = epoch;
     __threadfence_system();
 }
-struct HaloPull { float *dst[3]; const float *peer[2]; const unsigned *peer_flag[2]; int recv_i[2]; int lines, pitch, i_alloc0; unsigned epoch; int *bad; };
+struct HaloPull { float *dst[3]; const float *peer[2]; const unsigned *peer_flag[2]; int recv_i[2]; int lines, pitch, i_alloc0; unsigned epoch; int *bad;
+                  int field0, nf; };
 __global__ void k_halo_pull(HaloPull a)
 {
-    // grid: (pitch/4 / 256, lines, 6): z = side * 3 + field; side s reads the neighbour's region 1 - s
-    const int side = blockIdx.z / 3, field = blockIdx.z % 3;
+    // grid: (pitch/4 / 256, lines, 2 * nf): z = side * nf + (field - field0); side s reads the neighbour's region 1 - s
+    const int side = blockIdx.z / a.nf, field = a.field0 + blockIdx.z % a.nf;
     if (!a.peer[side]) return;
     __shared__ int ok;
     if (threadIdx.x == 0) {

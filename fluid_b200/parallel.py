@@ -154,6 +154,8 @@ class SlabFluid:
         if transport not in ("peer", "nccl"):
             raise ValueError("transport must be 'peer' or 'nccl'")
         self.transport = transport if nranks > 1 else "none"
+        self.overlap = False               # set_overlap(True): the exchange for step k+1 rides inside step k
+        self._ghost_fresh = False          # the ghost lines are what the neighbours hold now (only kept under overlap)
         if self.transport == "peer" and connect:
             self.connect_peers()
 
@@ -192,6 +194,18 @@ class SlabFluid:
     def close(self):
         self.f.close()
 
+    def set_overlap(self, on=True):
+        """FB_OPT_HALO_OVERLAP: fb_step_local refreshes the ghost lines for the next step while it finishes the current one
+        (U, V during the smoke passes, M during the interior of the last smoke pass, on a second stream), so that step()
+        exchanges explicitly only before the first step and after host-side changes.  Peer-memory transport between
+        processes only; bit-identical to the explicit exchange (tests/multi_gpu_check.py, bench.py's parity_check)."""
+        if on and self.nranks > 1 and self.transport != "peer":
+            raise ValueError("the overlapped exchange needs the peer-memory transport")
+        self.overlap = bool(on) and self.nranks > 1
+        self._ghost_fresh = False
+        if self.nranks > 1:
+            self.f.set_option(L.OPT_HALO_OVERLAP, 1 if self.overlap else 0)
+
     def edit(self, cmds):
         """Every rank applies the same (global-coordinate) commands; the kernels clip them
         to the lines the rank holds, ghosts included, so ghosts stay consistent."""
@@ -210,6 +224,7 @@ class SlabFluid:
 
     def exchange(self):
         self._ghost_stale = False
+        self._ghost_fresh = False
         if self.nranks == 1:
             return
         if self.transport == "peer":
@@ -232,8 +247,10 @@ class SlabFluid:
     def step(self, dt, nsteps=1, per_step=None):
         arr = E.pack(per_step) if per_step is not None and len(per_step) else None
         for _ in range(nsteps):
-            self.exchange()
+            if not (self.overlap and self._ghost_fresh):
+                self.exchange()
             self.step_no_exchange(dt, arr)
+            self._ghost_fresh = self.overlap      # the step left the next step's ghost lines behind
             if self._steps_since_check >= 16:
                 self.check_halo()
                 if self.adaptive_reach:
@@ -256,6 +273,7 @@ class SlabFluid:
         self.exchange()
         self.f.project(numIters, dt)
         self._ghost_stale = True      # only owned lines are solved: the ghost lines now lag one solve behind
+        self._ghost_fresh = False
 
     def check_halo(self):
         self._steps_since_check = 0

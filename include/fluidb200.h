@@ -293,10 +293,22 @@ int fb_profile_read(fb_handle *h, float *ms, int32_t *calls);
 /* Options.  FB_OPT_SOLVE_STATS (default 1): the fused red-black solvers also track the
  * per-iteration max |div| that fb_get_solve_stats reports (a few instructions per cell
  * update); throughput runs may switch it off. */
-typedef enum fb_option { FB_OPT_SOLVE_STATS = 0 } fb_option;
+/* FB_OPT_HALO_OVERLAP (default 0; slabs connected through fb_halo_connect only): fb_step_local itself refreshes the
+ * ghost lines for the NEXT step while it finishes this one -- U, V are packed, published and pulled on a second stream
+ * during the smoke passes, the last smoke pass computes the boundary strips first and M follows during its interior
+ * -- so consecutive fb_step_local calls need no fb_halo_exchange between them.  The caller still exchanges once before
+ * the first step and after anything else that changes U, V or M (edits from the host, fb_upload, fb_project). */
+typedef enum fb_option { FB_OPT_SOLVE_STATS = 0, FB_OPT_HALO_OVERLAP = 1 } fb_option;
 int fb_set_option(fb_handle *h, int32_t option, int32_t value);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int fb_launch_count(const fb_handle *h, uint64_t *count);
+/* Diagnostics (no counterpart in the reference).  The confinement pass computes its IEEE divisions and square roots
+ * (fluid.go:462-463, 474-480, 484, 509) with the instruction sequences of the hardware's own fast path written out as
+ * straight-line code, valid on a stated operand range and re-done with div.rn / sqrt.rn outside it.  This runs both on
+ * n random operand sets on `device`: mode 0 = random bit patterns, mode 1 = operands inside the accepted range; modes 2
+ * (random bit patterns) and 3 (tiny operands, subnormals included) test the fall-back's scaled sequences, which accept everything.
+ * counts6 = {quotients, accepted, accepted-and-different (must be 0), roots, accepted, accepted-and-different (must be 0)}. */
+int fb_selftest_fastmath(int32_t device, uint64_t n, uint32_t seed, int32_t mode, uint64_t *counts6);
 int fb_version(void);
 
 #ifdef __cplusplus

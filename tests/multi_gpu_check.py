@@ -28,8 +28,10 @@ def main():
     failures = 0
     cases = [presets.jet(256 * world, 192), presets.karman(200 * world, 160),
              presets.karman(240 * world, 128, bfecc=False, confinement=0.0)]
-    transports = ["peer", "peer", "nccl"]      # halo exchange: CUDA-IPC peer memory (default) and NCCL send/recv
-    for p, transport in zip(cases, transports):
+    # halo exchange: CUDA-IPC peer memory (explicit, then overlapped with the step: FB_OPT_HALO_OVERLAP) and NCCL send/recv
+    runs = [(cases[0], "peer", False), (cases[1], "peer", False), (cases[2], "nccl", False),
+            (cases[0], "peer", True), (cases[1], "peer", True), (cases[2], "peer", True)]
+    for p, transport, overlap in runs:
         bfecc = bool(p.params.get("use_bfecc", False))
         conf = float(p.params.get("confinement", 0.0))
         reach = 6
@@ -38,7 +40,11 @@ def main():
         slab.edit(p.init)
         slab.UseBFECC = bfecc
         slab.Confinement = conf
-        slab.step(p.dt, 30, p.per_step)
+        slab.set_overlap(overlap)
+        slab.step(p.dt, 13, p.per_step)
+        if overlap:                       # a host-side edit between overlapped steps reaches the ghost lines too
+            slab.edit(p.per_step)
+        slab.step(p.dt, 17, p.per_step)
         slab.check_halo()
         fields = {name: slab.get(name) for name in ("U", "V", "M", "p")}
         md = slab.MaxDivergence()
@@ -47,11 +53,15 @@ def main():
             single.edit(p.init)
             single.UseBFECC = bfecc
             single.Confinement = conf
-            single.step(p.dt, 30, p.per_step)
+            single.step(p.dt, 13, p.per_step)
+            if overlap:
+                single.edit(p.per_step)
+            single.step(p.dt, 17, p.per_step)
             for name, got in fields.items():
                 want = single.get(name)
                 bad = int(np.count_nonzero(~((got == want) | (np.isnan(got) & np.isnan(want)))))
-                print(f"[{p.name} {p.width}x{p.height} bfecc={bfecc} conf={conf} {transport}] {name}: mismatches={bad}")
+                print(f"[{p.name} {p.width}x{p.height} bfecc={bfecc} conf={conf} {transport}{' overlapped' if overlap else ''}] "
+                      f"{name}: mismatches={bad}")
                 failures += bad != 0
             assert np.float32(md) == np.float32(single.MaxDivergence())
             single.close()

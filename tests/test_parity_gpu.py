@@ -670,3 +670,56 @@ def test_ghost_zone_too_narrow_is_an_error():
     with pytest.raises(fluid_b200.FluidError):
         group.step(p.dt, 1, p.per_step)
     group.close()
+
+
+def test_fastmath_sequences_equal_the_ieee_instructions():
+    """k_confine_fast's straight-line division / square root against div.rn.f32 / sqrt.rn.f32 (fb_selftest_fastmath):
+    whatever operand the range test accepts must give the IEEE result bit for bit -- on random bit patterns (mode 0:
+    denormals, infinities, NaN included; most are rejected) and on operands drawn inside the range (mode 1: all accepted)."""
+    import ctypes as C
+    from fluid_b200 import _lib as L
+    for mode, n in ((0, 1 << 27), (1, 1 << 28), (2, 1 << 27), (3, 1 << 28)):
+        cnt = (C.c_uint64 * 6)()
+        rc = L.lib.fb_selftest_fastmath(0, n, 20261017 + mode, mode, cnt)
+        assert rc == 0
+        div_n, div_ok, div_diff, sq_n, sq_ok, sq_diff = [int(x) for x in cnt]
+        print(f"\nFASTMATH mode={mode} div: {div_n} drawn, {div_ok} accepted, {div_diff} differ; sqrt: {sq_n} drawn, {sq_ok} accepted, {sq_diff} differ")
+        assert div_n == n and sq_n == n
+        assert div_diff == 0 and sq_diff == 0
+        if mode >= 1:
+            assert div_ok == n and sq_ok == n
+        else:
+            assert div_ok > 0 and sq_ok > 0
+
+
+@pytest.mark.parametrize("phase", ["applyVorticityConfinement", "addTurbulence"])
+def test_confinement_operand_extremes_bit_exact(phase):
+    """The confinement pass on velocity fields whose magnitudes span the whole float32 range in patches -- exact zeros,
+    -0, denormals, 1e-38 .. 1e-20 (below the fast sequences' range: the IEEE fall-back must take over, per thread and per
+    CTA), ordinary values, and 1e15 .. 1e30 (above it; overflowing sums) -- against the oracle, bit for bit."""
+    from fluid_b200 import presets
+    p = presets.karman(300, 150)
+    o = developed_state(p, steps=5)
+    o.Confinement = 0.1
+    rng = np.random.default_rng(77)
+    nx, ny = o.NumX, o.NumY
+    scales = np.array([0.0, 1e-45, 1e-41, 1e-38, 1e-33, 1e-30, 1e-26, 1e-20, 1e-12, 1e-5, 1.0, 30.0, 1e8, 1e15, 1e19, 1e25, 1e30],
+                      dtype=np.float64)
+    for name in ("U", "V"):
+        # patches of 7 x 9 cells, each with its own scale (so neighbouring patches mix magnitudes at their seams)
+        pick = rng.integers(0, len(scales), size=(nx // 7 + 1, ny // 9 + 1))
+        sc = np.repeat(np.repeat(scales[pick], 7, axis=0), 9, axis=1)[:nx, :ny]
+        a = (rng.standard_normal((nx, ny)) * sc).astype(np.float32)
+        a[rng.random((nx, ny)) < 0.05] = np.float32(-0.0)
+        a[rng.random((nx, ny)) < 0.05] = np.float32(0.0)
+        o.set(name, a)
+    g = gpu_clone(o, p)
+    fn = dict(PHASES)[phase]
+    with np.errstate(all="ignore"):
+        fn(o, p.dt)
+    fn(g, p.dt)
+    for name in ("U", "V"):
+        got, want = g.get(name), o.get(name)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        assert_bit_exact(f"extremes/{phase}:{name}", got, want)
+    g.close()
