@@ -591,10 +591,14 @@ def run_preset(args, workload, rank, world, local, primary):
     def run_steps(n):
         sim.step(preset.dt, n, preset.per_step)
 
+    enqueue = []       # host time to queue a block (the host must stay ahead of the device: N > 1 steps from Python)
+
     def timed(n):
         barrier()
         sim.timer_start()
+        t0 = time.perf_counter()
         run_steps(n)
+        enqueue.append((time.perf_counter() - t0) * 1e3 / n)
         ms = sim.timer_stop()
         barrier()
         if world > 1:
@@ -707,6 +711,7 @@ def run_preset(args, workload, rank, world, local, primary):
         "timed_blocks_ms": blocks, "quiescent": {"ms_per_step": quiescent_ms / K, "value": cells_total * K / (quiescent_ms * 1e-3),
                                                 "what": f"the same {K} steps timed right after the warm-up, before the pre-roll"},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": clk,
+        "host_enqueue_ms_per_step": float(np.median(enqueue)) if enqueue else None,
     }
     if not primary:
         if world > 1:

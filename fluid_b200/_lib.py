@@ -36,8 +36,10 @@ PROF_PHASES = ("edits", "clear_pressure", "viscosity", "project", "confinement",
                "advect_velocity", "advect_smoke",
                # single kernels, one event pair per launch (inside the phase pairs above)
                "k_pressure_solve", "k_advect_velocity_full", "k_bfecc_velocity_correct", "k_advect_smoke_full",
-               "k_bfecc_smoke_correct", "k_confine_turbulence")
-PROF_KERNELS = PROF_PHASES[9:]
+               "k_bfecc_smoke_correct", "k_confine_turbulence",
+               # slabs: the halo exchange in front of a step, or (overlapped) the wait for it at the end of the step
+               "halo")
+PROF_KERNELS = PROF_PHASES[9:15]
 
 
 class Config(C.Structure):

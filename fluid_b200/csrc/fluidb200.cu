@@ -442,11 +442,21 @@ static bool halo_overlap_on(const fb_handle *h)
 static int halo_overlap_setup(fb_handle *h)
 {
     if (h->halo_stream) return FB_OK;
-    CK(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+    // highest priority: its few small blocks go in front of the smoke pass's as soon as an SM has room
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&h->halo_stream, cudaStreamNonBlocking, prio_hi));
     CK(cudaEventCreateWithFlags(&h->ev_ovl_uv, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_ovl_m, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_ovl_done, cudaEventDisableTiming));
     return FB_OK;
+}
+// fields [field0, field0 + nf) are final in the second stream's own order: exchange them there
+static int halo_exchange_on_second_stream(fb_handle *h, int field0, int nf, int word, unsigned epoch)
+{
+    const int buf = 2 + (int)(epoch & 1u);
+    TRY(halo_post_fields(h, h->halo_stream, buf, field0, nf, word, epoch));
+    return halo_pull_fields(h, h->halo_stream, buf, field0, nf, word, epoch);
 }
 // fields [field0, field0 + nf) are final on h->stream: exchange them on the second stream
 static int halo_overlap_fields(fb_handle *h, cudaEvent_t ev, int field0, int nf, int word, unsigned epoch)
@@ -460,6 +470,8 @@ static int halo_overlap_fields(fb_handle *h, cudaEvent_t ev, int field0, int nf,
 
 extern "C" int fb_halo_exchange(fb_handle *h)
 {
+    if (!h) return FB_ERR_INVALID;
+    ProfScope ps(h, FB_PROF_HALO);
     TRY(fb_halo_post(h));
     return fb_halo_pull(h);
 }
@@ -1404,6 +1416,7 @@ static int advect_velocity_fast(fb_handle *h, float dt, int ext = 0)
 // FB_OPT_HALO_OVERLAP) the boundary strips -- the lines the neighbours will pull -- go first, the exchange of M starts on the
 // second stream, and the interior follows.
 static int halo_overlap_fields(fb_handle *h, cudaEvent_t ev, int field0, int nf, int word, unsigned epoch);
+static int halo_exchange_on_second_stream(fb_handle *h, int field0, int nf, int word, unsigned epoch);
 static int smoke_final_pass(fb_handle *h, const fb_params *p, const AdvCtx &c, const float *srcM, float *outM, float dt, int ib, int ie,
                             bool overlap)
 {
@@ -1412,9 +1425,18 @@ static int smoke_final_pass(fb_handle *h, const fb_params *p, const AdvCtx &c, c
                          p->smoke_advection, p->viscosity_diffusion, ib, ie, h->d_bad);
         return FB_OK;
     }
+    // the strips run on the second (high-priority) stream, next to the interior launch on the handle's stream: two launches
+    // of ~130 CTAs in front of the interior cost a wave tail each
     const Grid &g = h->g;
     const int L = h->halo_lines;
     int lo = ib, hi = ie;                      // what is left for the interior launch
+    CK(cudaEventRecord(h->ev_ovl_m, h->stream));
+    CK(cudaStreamWaitEvent(h->halo_stream, h->ev_ovl_m, 0));
+    struct Restore {                           // the launch macros return on error: put the handle back whatever happens
+        fb_handle *h; cudaStream_t stream; float *M;
+        ~Restore() { h->stream = stream; h->f[FB_M] = M; }
+    } restore{h, h->stream, h->f[FB_M]};
+    h->stream = h->halo_stream;
     if (h->halo_peer[0] && hi - lo > L) {
         const int e = g.i_lo + L;
         ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, srcM, h->f[FB_NEWM], outM, dt,
@@ -1427,15 +1449,15 @@ static int smoke_final_pass(fb_handle *h, const fb_params *p, const AdvCtx &c, c
                          p->smoke_advection, p->viscosity_diffusion, b, hi, h->d_bad);
         hi = b;
     }
+    h->stream = restore.stream;
     const bool strips_done = (!h->halo_peer[0] || lo > ib) && (!h->halo_peer[1] || hi < ie);
-    float *const keepM = h->f[FB_M];
     h->f[FB_M] = outM;                        // what the pack reads and the pull writes
-    if (strips_done) TRY(halo_overlap_fields(h, h->ev_ovl_m, 2, 1, 2, ++h->ovl_epoch_m));
+    if (strips_done) TRY(halo_exchange_on_second_stream(h, 2, 1, 2, ++h->ovl_epoch_m));
     if (hi > lo)
         ADV_SMOKE_LAUNCH(c, h->f[FB_U], h->f[FB_V], h->mask, srcM, h->f[FB_NEWM], outM, dt,
                          p->smoke_advection, p->viscosity_diffusion, lo, hi, h->d_bad);
-    if (!strips_done) TRY(halo_overlap_fields(h, h->ev_ovl_m, 2, 1, 2, ++h->ovl_epoch_m));     // slab thinner than two strips
-    h->f[FB_M] = keepM;
+    if (!strips_done)                         // slab thinner than two strips: the whole pass first
+        TRY(halo_overlap_fields(h, h->ev_ovl_m, 2, 1, 2, ++h->ovl_epoch_m));
     return FB_OK;
 }
 
@@ -1759,6 +1781,7 @@ extern "C" int fb_step_local(fb_handle *h, const fb_params *p, float dt, int32_t
     if (ovl) {
         // whatever is queued on the handle's stream next sees the refreshed ghost lines: the next fb_step_local needs no
         // fb_halo_exchange (unless the host edits fields in between)
+        ProfScope ps(h, FB_PROF_HALO);
         CK(cudaEventRecord(h->ev_ovl_done, h->halo_stream));
         CK(cudaStreamWaitEvent(h->stream, h->ev_ovl_done, 0));
     }

@@ -286,6 +286,9 @@ typedef enum fb_prof_phase {
      * semi-Lagrangian passes (k_advect_*_full), the BFECC back-trace + correct passes, confinement + turbulence */
     FB_PROF_K_PRESSURE_SOLVE, FB_PROF_K_ADVECT_VELOCITY, FB_PROF_K_BFECC_VELOCITY, FB_PROF_K_ADVECT_SMOKE,
     FB_PROF_K_BFECC_SMOKE, FB_PROF_K_CONFINE_TURBULENCE,
+    /* slabs: fb_halo_exchange in front of a step, or -- with FB_OPT_HALO_OVERLAP -- how long the end of fb_step_local
+     * waits for the second stream's exchange */
+    FB_PROF_HALO,
     FB_PROF_NPHASES
 } fb_prof_phase;
 int fb_profile_enable(fb_handle *h, int32_t on);
