@@ -74,32 +74,85 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 5 ms from a thread (a 160 ms region gets
+    ~30 samples), `nvidia-smi -lms` when the NVML binding is missing (its fastest loop gives a handful)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* / nvmlClocksThrottleReason* bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device: int):
         self.device = device
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []          # (sm MHz, reasons bit mask)
+        self.sm_max = None
+        self.running = False
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.device < len(ids) and ids[self.device].isdigit():
+                return int(ids[self.device])
+        return self.device
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.source = "nvml, 5 ms"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
+                 str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 20"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), int(reasons(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=1.0)
+            sm = [x[0] for x in self.samples]
+            mask = 0
+            for x in self.samples:
+                mask |= x[1]
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
+                    "reasons": sorted(k for k, b in self.BITS.items() if mask & b), "source": self.source}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -122,7 +175,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": self.source}
 
 
 def make_fluid(mod, preset, solver, **kw):
@@ -574,6 +627,7 @@ def run_preset(args, workload, rank, world, local, primary):
         sim.UseBFECC = bfecc
         sim.Confinement = conf
         sim.adaptive_reach = True       # reach (hence the ghost lines every phase recomputes) follows the all-reduced max |u|
+        sim.check_every = 64            # halo check + reach update: a stream drain and an all-reduce each time
         overlap = args.transport == "peer" and not args.no_overlap
         sim.set_overlap(overlap)        # the exchange for step k+1 rides inside step k (FB_OPT_HALO_OVERLAP)
         cells_total = sim.global_cells
@@ -582,7 +636,7 @@ def run_preset(args, workload, rank, world, local, primary):
         when = ("overlapped with the step: U, V travel on a second stream during the smoke passes, M during the interior of the last "
                 "smoke pass, whose boundary strips are computed first" if overlap else "in front of the step")
         parallelism = (f"row slabs over i, {world} ranks, {ghost} ghost lines allocated (reach for |u| <= 8), the reach used per step "
-                       f"re-measured every 16 steps from the all-reduced max |u| x 1.5; 1 halo exchange per step {how}, {when}")
+                       f"re-measured every 64 steps from the all-reduced max |u| x 1.5; 1 halo exchange per step {how}, {when}")
     else:
         sim = make_fluid(fluid_b200, preset, solver, device=local)
         cells_total = sim.NumX * sim.NumY

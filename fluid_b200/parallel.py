@@ -141,6 +141,7 @@ class SlabFluid:
         self.rank, self.nranks, self.device = rank, nranks, device
         self.reach = self.reach_cap = reach
         self.adaptive_reach = False        # bench.py / callers opt in; the tests pin the reach they were written for
+        self.check_every = 16              # steps between halo checks (+ reach updates): each one drains the stream
         self.f = Fluid(density, width, height, h, device=device, solver=solver, rank=rank, nranks=nranks,
                        ghost=ghost if nranks > 1 else 0)
         self.NumX, self.NumY = self.f.NumX, self.f.NumY
@@ -251,7 +252,7 @@ class SlabFluid:
                 self.exchange()
             self.step_no_exchange(dt, arr)
             self._ghost_fresh = self.overlap      # the step left the next step's ghost lines behind
-            if self._steps_since_check >= 16:
+            if self._steps_since_check >= self.check_every:
                 self.check_halo()
                 if self.adaptive_reach:
                     self.adapt_reach(dt)
@@ -259,7 +260,7 @@ class SlabFluid:
     def adapt_reach(self, dt):
         """size the semi-Lagrangian reach from the all-reduced max |u| instead of a constant.  Every phase
         of fb_step_local is recomputed on as many ghost lines as the reach asks for, so a reach that follows the flow
-        (with a 1.5x margin, re-measured every 16 steps together with the halo check) trims the redundant work; a trace
+        (with a 1.5x margin, re-measured every `check_every` steps together with the halo check) trims the redundant work; a trace
         that outruns it still raises FB_ERR_HALO at the next check, never a wrong result.  Never above the reach the
         ghost zone was allocated for."""
         speed = self.max_speed()

@@ -39,7 +39,7 @@ build)
                     nl32w4s2 "-DRQ_NL=32 -DRQ_WSTG=4 -DRQ_LSPLIT=2 -DRQ_WSPLIT=2" ;;
 run)
   for v in base nl28w4 nl32w4 nl34w4 nl36w4 wl256x2 wl256deep ls2ws2 ls4ws4 nl32w4s2; do
-    echo -n "$v: "; FLUIDB200_LIB=$PWD/tools/variants/lib_$v.so timeout 40 python tools/rbq_iters.py 1 8 2>&1 | tail -1
+    echo -n "$v: "; FLUIDB200_LIB=$PWD/fluid_b200/variants/lib_$v.so timeout 40 python tools/rbq_iters.py 1 8 2>&1 | tail -1
   done ;;
 *) echo "usage: $0 build|run"; exit 2 ;;
 esac
