@@ -209,7 +209,7 @@ __device__ __forceinline__ void rq_tma_load(unsigned dst, const void *src, unsig
 // Bounded waits: a pipeline that stops making progress must never hang the GPU.  After ~2^21 failed polls
 // (hundreds of milliseconds) the first waiter records who waited for what in P.debug and every waiter
 // falls through; the host turns the flag into an error.
-__device__ int *rq_debug;   // set per launch (RBQ::debug)
+__shared__ int *rq_debug;   // per CTA, set by thread 0 at kernel entry (RBQ::debug): handles on one device never share it
 __device__ __noinline__ void rq_wait_slow(unsigned bar, unsigned parity, int tag)
 {
     for (unsigned trip = 0;; trip++) {
