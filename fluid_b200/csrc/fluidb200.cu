@@ -1265,8 +1265,9 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         }
         WL = RQ_WL;
         if (!h->rbq_attr_set) {
-            CK(cudaFuncSetAttribute(k_rbq_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CK(cudaFuncSetAttribute(k_rbq_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            // static shared memory (the per-CTA debug pointer) counts against the 227 KB too
+            CK(cudaFuncSetAttribute(k_rbq_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            CK(cudaFuncSetAttribute(k_rbq_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
             h->rbq_attr_set = true;
         }
     }

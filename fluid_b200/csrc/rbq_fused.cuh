@@ -209,7 +209,11 @@ __device__ __forceinline__ void rq_tma_load(unsigned dst, const void *src, unsig
 // Bounded waits: a pipeline that stops making progress must never hang the GPU.  After ~2^21 failed polls
 // (hundreds of milliseconds) the first waiter records who waited for what in P.debug and every waiter
 // falls through; the host turns the flag into an error.
+#ifdef RQ_DEBUG_GLOBAL
+__device__ int *rq_debug;   // round-1 form (one module-global for all handles); kept for A/B
+#else
 __shared__ int *rq_debug;   // per CTA, set by thread 0 at kernel entry (RBQ::debug): handles on one device never share it
+#endif
 __device__ __noinline__ void rq_wait_slow(unsigned bar, unsigned parity, int tag)
 {
     for (unsigned trip = 0;; trip++) {
@@ -237,14 +241,36 @@ __device__ __forceinline__ void rq_wait_a(unsigned bar, unsigned parity, int tag
         if (rq_mbar_try_a(bar, parity)) return;
     rq_wait_slow(bar, parity, tag);
 }
-// line / step `line` of the role whose ring starts at `ring`
+// line / step `line` of the role whose ring starts at `ring`.  RQ_ELECT (experiment): ONE lane per warp arrives (after
+// __syncwarp, which orders the other lanes' stores before its release) and one lane polls (the others take the acquire
+// through the __syncwarp behind it): 32x fewer operations on the hand-off word.  Call sites are warp-uniform.
+#ifndef RQ_ELECT
+#define RQ_ELECT 0
+#endif
+#define RQ_ARRIVALS (RQ_ELECT ? 1 : 32)      // arrivals per warp and hand-off
 __device__ __forceinline__ void rq_wait_line(unsigned ring, int line, int tag)
+{
+#if RQ_ELECT
+    if ((threadIdx.x & 31) == 0)
+        rq_wait_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)), (unsigned)(line >> RQ_RING_LOG2) & 1u, tag | line);
+    __syncwarp();
+#else
+    rq_wait_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)), (unsigned)(line >> RQ_RING_LOG2) & 1u, tag | line);
+#endif
+}
+// the same wait for a call site that only ONE lane reaches (the TMA issuers)
+__device__ __forceinline__ void rq_wait_line_one(unsigned ring, int line, int tag)
 {
     rq_wait_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)), (unsigned)(line >> RQ_RING_LOG2) & 1u, tag | line);
 }
 __device__ __forceinline__ void rq_done_line(unsigned ring, int line)
 {
+#if RQ_ELECT
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) rq_arrive_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)));
+#else
     rq_arrive_a(ring + 8u * (unsigned)(line & (RQ_RING - 1)));
+#endif
 }
 
 // ---- one cell update, four cells at a time -------------------------------------------------------
@@ -446,7 +472,7 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
     // arrivals per phase: every lane of the warp(s) that own the line / step
     for (int k = tid; k < RQ_ROLES * RQ_RING; k += RQ_THREADS) {
         const int role = k / RQ_RING;
-        rq_mbar_init(bars + k, role == 0 ? 32 * RQ_LSPLIT : (role == RQ_WROLE ? 32 * RQ_WSPLIT : 32 * RQ_SPLIT));
+        rq_mbar_init(bars + k, RQ_ARRIVALS * (role == 0 ? RQ_LSPLIT : (role == RQ_WROLE ? RQ_WSPLIT : RQ_SPLIT)));
     }
     if (tid >= 32 && tid < 32 + RQ_STG) rq_mbar_init(full + tid - 32, 1);
     if (tid >= 64 && tid < 64 + RQ_WSTG) rq_mbar_init(wfull + tid - 64, 1);
@@ -580,10 +606,10 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             __syncwarp();                                    // every lane is done with staging slot st0
             if (l_issuer && rel + RQ_STG <= nproc) {
 #if RQ_LSPLIT > 1
-                rq_wait_line(ring_ld, rel, 36 << 20);                         // the other warps of this line
+                rq_wait_line_one(ring_ld, rel, 36 << 20);                         // the other warps of this line
 #endif
                 // the slot also was the "line above" of line rel-1, which another loader warp handles
-                if (rel >= 1) rq_wait_line(ring_ld, rel - 1, 35 << 20);
+                if (rel >= 1) rq_wait_line_one(ring_ld, rel - 1, 35 << 20);
                 stage_line(rel + RQ_STG);
             }
             sl += LGRP; if (sl >= RQ_NL) sl -= RQ_NL;
@@ -707,7 +733,7 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             __syncwarp();
 #if RQ_WSPLIT > 1
             if (w_issuer && n + RQ_WSTG < i1c - i0c) {
-                rq_wait_line(ring_wr, rel, 37 << 20);                         // the other warps of this line
+                rq_wait_line_one(ring_wr, rel, 37 << 20);                         // the other warps of this line
                 stage_line(n + RQ_WSTG);
             }
 #else
