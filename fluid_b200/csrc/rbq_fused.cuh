@@ -343,11 +343,18 @@ struct RQStage {
 // One step.  P2 (in: q_old[rel-1][A], out: the `up` loaded now), P1 (q_old[rel][1-A]), F2 (in: first(rel-2),
 // out: first(rel)), F1 (first(rel-1)).  FIRST is false only for the step past the last line (line e1 is never
 // swept and reads as q = 0), SECOND only for step 0.
-template <int A, bool FIRST, bool SECOND, bool STATS>
+// RQ_PAIRWAIT (experiment): iterations 1 .. 7 wait for their predecessor once per TWO steps (for its step rel+3, which
+// implies rel+2: a stage finishes its steps in order) instead of once per step; needs RQ_NL >= 32.  Iteration 0 keeps one
+// wait per step: the loader's warps finish their lines in any order.
+#ifndef RQ_PAIRWAIT
+#define RQ_PAIRWAIT 0
+#endif
+template <int A, bool FIRST, bool SECOND, bool STATS, bool WAIT = true>
 __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (&P2)[RQ_Q], float4 (&P1)[RQ_Q], float4 (&F2)[RQ_Q],
                                              const float4 (&F1)[RQ_Q])
 {
-    {   // the loader has finished line rel+1 / the previous iteration has finished its step rel+2
+    if (WAIT || S.lag == 1) {
+        // the loader has finished line rel+1 / the previous iteration has finished its step rel+2
         // (the loader's warps take the lines in turn, so "line 1 is loaded" says nothing about line 0: the
         // first step of the first iteration waits for both; every later line was waited for one step earlier)
         if (!SECOND && S.lag == 1) rq_wait_line(S.pred, 0, S.tag);
@@ -425,7 +432,7 @@ __device__ __forceinline__ void rq_pair_stage(RQStage &S)
     int rel = 1;
     for (; rel + 1 < nproc; rel += 2) {
         rq_pair_step<1 - A0, true, true, STATS>(S, rel, pb, pa, fb, fa);
-        rq_pair_step<A0, true, true, STATS>(S, rel + 1, pa, pb, fa, fb);
+        rq_pair_step<A0, true, true, STATS, !RQ_PAIRWAIT>(S, rel + 1, pa, pb, fa, fb);
     }
     if (rel < nproc) {
         rq_pair_step<1 - A0, true, true, STATS>(S, rel, pb, pa, fb, fa);
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
         { const float c1 = P.wd[2 * t] * 0.25f, c2 = P.wd[2 * t + 1] * 0.25f; S.c41 = make_float2(c1, c1); S.c42 = make_float2(c2, c2); }
         S.tw1 = tblw + 8 * (2 * t); S.tw2 = tblw + 8 * (2 * t + 1);
         S.pred = rq_s32(bars + t * RQ_RING); S.mine = rq_s32(bars + (1 + t) * RQ_RING);
-        S.lag = t == 0 ? 1 : 2; S.nproc = nproc; S.tag = t << 20; S.bar_id = 1 + t;
+        S.lag = t == 0 ? 1 : (RQ_PAIRWAIT ? 3 : 2); S.nproc = nproc; S.tag = t << 20; S.bar_id = 1 + t;
         S.e_dn = (RQ_NL - 1) * ROW; S.e_own = 0; S.e_up = ROW; S.sl_up = 1; S.ROW = ROW;
         S.i0r = own0; S.i1r = i1c - e0;
         S.skip = (P.xflags & 1) != 0;
