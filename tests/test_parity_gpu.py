@@ -612,7 +612,12 @@ def test_pressure_form_many_chunks_bit_exact_and_deterministic():
         g = fluid_b200.New(p.density, p.width, p.height, p.h, solver=2)
         prepare(g)
         g.project(8, p.dt)
-        assert_state_equal(g, cpu, "many chunks", fields=("U", "V", "p"))
+        for name in ("U", "V", "p"):       # a failure says WHERE (a hand-off race shows in particular lines of a chunk)
+            got, want = g.get(name), cpu.get(name)
+            d = np.argwhere(~((got == want) | (np.isnan(got) & np.isnan(want))))      # +0 / -0 compare equal, as in assert_bit_exact
+            assert len(d) == 0, (f"many chunks, solve {len(runs)}, {name}: {len(d)} cells differ; lines {d[:, 0].min()}..{d[:, 0].max()} "
+                                 f"(first distinct: {np.unique(d[:, 0])[:16].tolist()}), columns {d[:, 1].min()}..{d[:, 1].max()} "
+                                 f"(first distinct: {np.unique(d[:, 1])[:16].tolist()}); tools/rbq_race_hunt.py repeats this solve")
         runs.append(g.get("p"))
         g.close()
     assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
