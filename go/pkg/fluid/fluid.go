@@ -74,6 +74,11 @@ type Fluid struct {
 	uvOK     bool            // the U, V mirrors reflect the device (SampleVelocity is served from them)
 	frame    int             // which pinned frame buffer the view in flight targets (BeginSmoke)
 	frameBuf []float32
+	// display frame of BeginSmokeFrame: C-allocated bytes (the asynchronous copy outlives the cgo call, so it must not
+	// target Go memory) and their shape
+	shotC                           unsafe.Pointer
+	shot                            []byte
+	shotLines, shotCols, shotStride int
 }
 
 func check(h *C.fb_handle, st C.int) {
@@ -125,7 +130,12 @@ func newFluid(density float32, width, height int, h float32, flags C.int32_t) *F
 	}
 	f.U, f.V = mirror(handle, C.FB_U), mirror(handle, C.FB_V)
 	f.S, f.M = mirror(handle, C.FB_S), mirror(handle, C.FB_M)
-	runtime.SetFinalizer(f, func(f *Fluid) { C.fb_destroy(f.h) })
+	runtime.SetFinalizer(f, func(f *Fluid) {
+		C.fb_destroy(f.h) // waits for the copy stream, so nothing writes the display buffer any more
+		if f.shotC != nil {
+			C.free(f.shotC)
+		}
+	})
 	return f
 }
 
@@ -376,6 +386,44 @@ func (f *Fluid) EndSmoke() ScalarField {
 	var mn, mx C.float
 	check(f.h, C.fb_view_end(f.h, &mn, &mx))
 	return ScalarField{NumX: f.NumX, NumY: f.NumY, values: f.frameBuf, MinValue: float32(mn), MaxValue: float32(mx)}
+}
+
+// DisplayFrame is what BeginSmokeFrame / EndSmokeFrame deliver: every Stride-th cell of every Stride-th line of the
+// Smoke() view as one byte, quantised on the device against the FULL field's MinValue / MaxValue
+// (byte = round(255 (v - min) / (max - min))); Pix[i*Cols+j] shows cell (i*Stride, j*Stride).  For windows smaller
+// than the grid (main/ draws one pixel per cell): 1/(4 Stride^2) of the bytes of EndSmoke's float field.
+type DisplayFrame struct {
+	Lines, Cols, Stride int
+	Pix                 []byte
+	MinValue, MaxValue  float32
+}
+
+// BeginSmokeFrame is BeginSmoke for a display frame (fb_view_u8_begin).  The bytes land in a C-allocated buffer: the
+// copy completes after the cgo call returns (at EndSmokeFrame), and Go memory may only be lent to C for the
+// duration of a call.  EndSmokeFrame's Pix aliases that buffer until the next BeginSmokeFrame.
+func (f *Fluid) BeginSmokeFrame(stride int) {
+	f.flush()
+	if stride < 1 {
+		panic("fluid: stride must be >= 1")
+	}
+	lines, cols := (f.NumX+stride-1)/stride, (f.NumY+stride-1)/stride
+	if len(f.shot) != lines*cols {
+		if f.shotC != nil {
+			C.free(f.shotC)
+		}
+		f.shotC = C.malloc(C.size_t(lines * cols))
+		f.shot = unsafe.Slice((*byte)(f.shotC), lines*cols)
+	}
+	var l, c C.int32_t
+	check(f.h, C.fb_view_u8_begin(f.h, C.FB_VIEW_SMOKE, C.int32_t(stride), (*C.uint8_t)(f.shotC), &l, &c))
+	f.shotLines, f.shotCols, f.shotStride = int(l), int(c), stride
+}
+
+func (f *Fluid) EndSmokeFrame() DisplayFrame {
+	var mn, mx C.float
+	check(f.h, C.fb_view_end(f.h, &mn, &mx))
+	return DisplayFrame{Lines: f.shotLines, Cols: f.shotCols, Stride: f.shotStride, Pix: f.shot,
+		MinValue: float32(mn), MaxValue: float32(mx)}
 }
 
 // ---- the frame loop either side of Simulate: main/'s Draw pixel pass and advectParticles ------
