@@ -109,3 +109,53 @@ def test_halo_exchange_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_slab_step_exchanges_only_when_the_ghost_lines_are_stale():
+    """Host logic of SlabFluid.step (no GPU): with the exchange in front of the step every step exchanges; with the
+    overlapped exchange (FB_OPT_HALO_OVERLAP) only the first step does, and again after project(), which leaves the
+    ghost lines one solve behind; the halo check runs every `check_every` steps."""
+    from fluid_b200 import parallel
+
+    class Stub(parallel.SlabFluid):
+        def __init__(self):                      # none of the device state
+            object.__setattr__(self, "log", [])
+            self.nranks, self.transport, self.overlap = 2, "peer", False
+            self._ghost_fresh, self._ghost_stale, self._steps_since_check = False, False, 0
+            self.check_every, self.adaptive_reach, self.reach = 4, False, 6
+
+            class F:                             # what project() / set_overlap() touch
+                def project(_, n, dt): self.log.append("solve")
+                def set_option(_, o, v): self.log.append(("option", o, v))
+            self.f = F()
+
+        def exchange(self):
+            self.log.append("exchange")
+            self._ghost_stale = self._ghost_fresh = False
+
+        def step_no_exchange(self, dt, per_step=None):
+            self.log.append("step")
+            self._steps_since_check += 1
+
+        def check_halo(self):
+            self.log.append("check")
+            self._steps_since_check = 0
+
+    s = Stub()
+    s.step(0.01, 3)
+    assert s.log == ["exchange", "step"] * 3
+    s.log.clear()
+    s.set_overlap(True)
+    s.step(0.01, 5)
+    assert s.log == [("option", parallel.L.OPT_HALO_OVERLAP, 1), "exchange", "step", "check", "step", "step", "step", "step", "check"]
+    s.log.clear()
+    s.project(8, 0.01)                           # exchanges for itself, then the ghost lines lag
+    s.step(0.01, 2)
+    assert s.log == ["exchange", "solve", "exchange", "step", "step"]
+    s.log.clear()
+    s.set_overlap(False)
+    s.step(0.01, 2)
+    assert s.log == [("option", parallel.L.OPT_HALO_OVERLAP, 0), "exchange", "step", "exchange", "step", "check"]
+    with pytest.raises(ValueError):
+        s.transport = "nccl"
+        s.set_overlap(True)
