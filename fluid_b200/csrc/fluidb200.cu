@@ -1294,6 +1294,12 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
         a.stats = h->d_red;
         a.debug = reinterpret_cast<int *>(h->d_red + 48);
         { const char *x = getenv("FLUIDB200_RBQ_X"); a.xflags = x ? atoi(x) : 0; }
+#ifdef RQ_TRACE
+        static long long *d_trace = nullptr;
+        if (!d_trace) CK(cudaMalloc(&d_trace, 10 * 512 * 4 * sizeof(long long)));
+        CK(cudaMemsetAsync(d_trace, 0, 10 * 512 * 4 * sizeof(long long), h->stream));
+        a.trace = d_trace;
+#endif
         const bool last = done + k == iters;
         if (fuse_turbulence && last) {
             volatile float ts = p->turbulence_strength * dt;
@@ -1310,6 +1316,14 @@ static int project_redblack_fused(fb_handle *h, const fb_params *p, float dt, un
             if (h->want_stats) k_rbq_fused<true><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
             else k_rbq_fused<false><<<dim3(nstrips, nchunks, 1), RQ_THREADS, smem_q, h->stream>>>(a);
             CKL("k_rbq_fused");
+#ifdef RQ_TRACE
+            if (const char *path = getenv("FLUIDB200_RBQ_TRACE")) {
+                std::vector<long long> host(10 * 512 * 4);
+                CK(cudaMemcpyAsync(host.data(), a.trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                if (FILE *fp = fopen(path, "wb")) { fwrite(host.data(), sizeof(long long), host.size(), fp); fclose(fp); }
+            }
+#endif
         }
         give_plane(h, h->f[FB_U]); give_plane(h, h->f[FB_V]); give_plane(h, h->f[FB_P]);
         h->f[FB_U] = Uo; h->f[FB_V] = Vo; h->f[FB_P] = Po;

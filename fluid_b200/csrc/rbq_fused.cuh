@@ -149,7 +149,15 @@ struct RBQ {
     int xflags;                  // experiments (FLUIDB200_RBQ_X): 1 skip sweeps, 2 skip writer I/O, 4 skip TMA, 8 / 16 skip the loader's reads / stores
     const float *noiseU, *noiseV;
     float turb;
+#ifdef RQ_TRACE
+    long long *trace;            // [role 0 .. 9][line 0 .. 511][4] clock64 stamps of CTA (0, 0)
+#endif
 };
+#ifdef RQ_TRACE
+#define RQ_T(role, line, k) do { if (P_trace && (threadIdx.x & 31) == 0 && (line) >= 0 && (line) < 512) P_trace[(((role) * 512) + (line)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define RQ_T(role, line, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ unsigned rq_s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rq_mbar_init(unsigned long long *bar, int count)
@@ -327,6 +335,9 @@ __device__ __forceinline__ void rq_stat(const float4 qo, const float4 t, const u
 }
 
 struct RQStage {
+#ifdef RQ_TRACE
+    long long *trace; int role;
+#endif
     float *sQ; const unsigned char *sC;
     int WQ, NDO, lane4, lane, TJ;
     float2 nwd1, c41, nwd2, c42;        // (-wd, -wd) and (wd/4, wd/4) of the two half sweeps
@@ -346,6 +357,14 @@ struct RQStage {
 // RQ_PAIRWAIT (experiment): iterations 1 .. 7 wait for their predecessor once per TWO steps (for its step rel+3, which
 // implies rel+2: a stage finishes its steps in order) instead of once per step; needs RQ_NL >= 32.  Iteration 0 keeps one
 // wait per step: the loader's warps finish their lines in any order.
+#ifndef RQ_WEARLY
+#define RQ_WEARLY 0        // experiment: the writer frees a line's ring slots before it computes and stores (see the writer)
+#endif
+#ifndef RQ_WUNROLL
+#define RQ_WUNROLL 2
+#endif
+#define RQ_PRAGMA_(x) _Pragma(#x)
+#define RQ_PRAGMA(x) RQ_PRAGMA_(x)
 #ifndef RQ_PAIRWAIT
 #define RQ_PAIRWAIT 0
 #endif
@@ -353,6 +372,10 @@ template <int A, bool FIRST, bool SECOND, bool STATS, bool WAIT = true>
 __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (&P2)[RQ_Q], float4 (&P1)[RQ_Q], float4 (&F2)[RQ_Q],
                                              const float4 (&F1)[RQ_Q])
 {
+#ifdef RQ_TRACE
+    long long *const P_trace = S.trace;
+    RQ_T(S.role, rel, 0);
+#endif
     if (WAIT || S.lag == 1) {
         // the loader has finished line rel+1 / the previous iteration has finished its step rel+2
         // (the loader's warps take the lines in turn, so "line 1 is loaded" says nothing about line 0: the
@@ -360,9 +383,15 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
         if (!SECOND && S.lag == 1) rq_wait_line(S.pred, 0, S.tag);
         rq_wait_line(S.pred, min(rel + S.lag, S.nproc), S.tag);
     }
+#ifdef RQ_TRACE
+    RQ_T(S.role, rel, 1);
+#endif
     // the stores of the previous step by the other lanes of the stage (left / right neighbours of `second`)
     if (RQ_SPLIT > 1) asm volatile("bar.sync %0, %1;" ::"r"(S.bar_id), "n"(32 * RQ_SPLIT) : "memory");
     else __syncwarp();
+#ifdef RQ_TRACE
+    RQ_T(S.role, rel, 2);
+#endif
     float *const sQ = S.sQ;
     const int own = S.e_own + A * S.WQ + S.lane4, oth = S.e_own + (1 - A) * S.WQ + S.lane4;
     const int upo = S.e_up + A * S.WQ + S.lane4;
@@ -415,6 +444,9 @@ __device__ __forceinline__ void rq_pair_step(RQStage &S, const int rel, float4 (
         }
     }
     rq_done_line(S.mine, rel);
+#ifdef RQ_TRACE
+    RQ_T(S.role, rel, 3);
+#endif
     S.e_dn = S.e_own; S.e_own = S.e_up;
     if (++S.sl_up == RQ_NL) { S.sl_up = 0; S.e_up = 0; } else S.e_up += S.ROW;
 }
@@ -508,6 +540,9 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
         S.i0r = own0; S.i1r = i1c - e0;
         S.skip = (P.xflags & 1) != 0;
         S.mymax = 0.0f;
+#ifdef RQ_TRACE
+        S.trace = (blockIdx.x == 0 && blockIdx.y == 0 && hw == 0) ? P.trace : nullptr; S.role = 1 + t;
+#endif
         if ((colour + e0) & 1) rq_pair_stage<1, STATS>(S); else rq_pair_stage<0, STATS>(S);
         if (STATS) {
             const float mymax = warp_max(S.mymax);
@@ -565,6 +600,10 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
         for (int rel = lgrp; rel <= nproc; rel += LGRP) {
             // slot(rel) last held line y-1 with y = rel - NL + 1.  Its readers: the stages up to the last one's step y
             // (which writes line y-1 for the last time) and, for owned lines, the writer at lines y-1 and y.
+#ifdef RQ_TRACE
+            long long *const P_trace = (blockIdx.x == 0 && blockIdx.y == 0) ? P.trace : nullptr;
+            RQ_T(0, rel, 0);
+#endif
             const int y = rel - RQ_NL + 1;
             if (y >= 0) {
                 if (y - 1 >= own0 && y - 1 <= last_owned) rq_wait_line(ring_wr, y - 1, 40 << 20);
@@ -575,6 +614,9 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             const int st0 = rel & (RQ_STG - 1), st1 = (rel + 1) & (RQ_STG - 1);
             rq_wait_a(b_full + 8u * (unsigned)st0, (unsigned)(rel / RQ_STG) & 1u, (30 << 20) | rel);
             if (rel < nproc) rq_wait_a(b_full + 8u * (unsigned)st1, (unsigned)((rel + 1) / RQ_STG) & 1u, (31 << 20) | rel);
+#ifdef RQ_TRACE
+            RQ_T(0, rel, 1);
+#endif
             const bool live = rel >= live_lo && rel <= live_hi;
             const unsigned char *s0 = stg + st0 * STG, *s1 = stg + st1 * STG;
             const int e_slot = sl * ROW;
@@ -610,6 +652,9 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
                 *reinterpret_cast<unsigned short *>(sC + b1) = (unsigned short)__byte_perm(code, 0u, 0x4431);
             }
             rq_done_line(ring_ld, rel);
+#ifdef RQ_TRACE
+            RQ_T(0, rel, 2);
+#endif
             __syncwarp();                                    // every lane is done with staging slot st0
             if (l_issuer && rel + RQ_STG <= nproc) {
 #if RQ_LSPLIT > 1
@@ -619,6 +664,9 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
                 if (rel >= 1) rq_wait_line_one(ring_ld, rel - 1, 35 << 20);
                 stage_line(rel + RQ_STG);
             }
+#ifdef RQ_TRACE
+            RQ_T(0, rel, 3);
+#endif
             sl += LGRP; if (sl >= RQ_NL) sl -= RQ_NL;
         }
     } else if (warp < RQ_SW + RQ_LW + RQ_WW) {
@@ -668,12 +716,37 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
             for (int n = wgrp; n < RQ_WSTG && n < i1c - i0c; n += WGRP) stage_line(n);
         for (int n = wgrp; n < i1c - i0c; n += WGRP) {
             const int r = i0c + n, rel = r - e0;
+#ifdef RQ_TRACE
+            long long *const P_trace = (blockIdx.x == 0 && blockIdx.y == 0) ? P.trace : nullptr;
+            RQ_T(9, rel, 0);
+#endif
             rq_wait_line(ring_last, rel + 1, nst << 20);                // the last iteration has finished its step rel+1: line r is final
             const int ws = n & (RQ_WSTG - 1);
             rq_wait_a(b_wfull + 8u * (unsigned)ws, (unsigned)(n / RQ_WSTG) & 1u, (32 << 20) | rel);   // U0, V0, mask of line r have landed
+#ifdef RQ_TRACE
+            RQ_T(9, rel, 1);
+#endif
             const int e_line = sl * ROW, e_linem = (sl == 0 ? RQ_NL - 1 : sl - 1) * ROW;
             const bool line_first = (r == 0);
-#pragma unroll 2
+#if RQ_WEARLY
+            // RQ_WEARLY: everything the writer reads of the RING (q of lines r and r-1) goes into registers first and the
+            // slots are handed back at once; U0, V0, mask come from the writer's own staging ring.  The time a line occupies
+            // its slot, not the writer's throughput, is what the closed loader -> sweeps -> writer loop is short of.
+            float2 r_ev[WCG], r_od[WCG], r_evm[WCG], r_odm[WCG];
+            float r_ql[WCG];
+#pragma unroll
+            for (int cgi = 0; cgi < WCG; cgi++) {
+                const int st = lane + 32 * (wpart * WCG + cgi);
+                const int q = (RQ_H + 4 * st) >> 1, e_row = e_line + q, e_rowm = e_linem + q;
+                r_ev[cgi] = *reinterpret_cast<const float2 *>(sQ + e_row);
+                r_od[cgi] = *reinterpret_cast<const float2 *>(sQ + e_row + WQ);
+                r_evm[cgi] = *reinterpret_cast<const float2 *>(sQ + e_rowm);
+                r_odm[cgi] = *reinterpret_cast<const float2 *>(sQ + e_rowm + WQ);
+                r_ql[cgi] = sQ[e_row + WQ - 1];
+            }
+            rq_done_line(ring_wr, rel);                               // the slots of line r are free
+#endif
+RQ_PRAGMA(unroll RQ_WUNROLL)
             for (int cgi = 0; cgi < WCG; cgi++) {
                 const int cg = wpart * WCG + cgi;
                 const int st = lane + 32 * cg;
@@ -687,11 +760,17 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
                 const unsigned m4 = *reinterpret_cast<const unsigned *>(sb + 2 * oV - 12 * st);
                 float pin[4] = {0.f, 0.f, 0.f, 0.f};
                 if (P.Pin) unpack(ld4(P.Pin + o), pin);
+#if RQ_WEARLY
+                const float2 ev = r_ev[cgi], od = r_od[cgi], evm = r_evm[cgi], odm = r_odm[cgi];
+                const float ql = r_ql[cgi];
+                (void)e_row; (void)e_rowm;
+#else
                 const float2 ev = *reinterpret_cast<const float2 *>(sQ + e_row);
                 const float2 od = *reinterpret_cast<const float2 *>(sQ + e_row + WQ);
                 const float2 evm = *reinterpret_cast<const float2 *>(sQ + e_rowm);
                 const float2 odm = *reinterpret_cast<const float2 *>(sQ + e_rowm + WQ);
                 const float ql = sQ[e_row + WQ - 1];                   // column lj-1 (odd parity, index q-1)
+#endif
                 const float qc[4] = { ev.x, od.x, ev.y, od.y }, qx[4] = { evm.x, odm.x, evm.y, odm.y };
                 const float uu[4] = { u.x, u.y, u.z, u.w }, vv[4] = { v.x, v.y, v.z, v.w };
                 float pu[4], pv[4], pp[4];
@@ -736,7 +815,12 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB) k_rbq_fused(const RBQ P)
                     for (int k = 0; k < 4 && w_j + k < NY; k++) { P.Uo[o + k] = pu[k]; P.Vo[o + k] = pv[k]; P.Po[o + k] = pp[k]; }
                 }
             }
+#if !RQ_WEARLY
             rq_done_line(ring_wr, rel);                               // the slots of line r are free
+#endif
+#ifdef RQ_TRACE
+            RQ_T(9, rel, 2);
+#endif
             __syncwarp();
 #if RQ_WSPLIT > 1
             if (w_issuer && n + RQ_WSTG < i1c - i0c) {
